@@ -1,0 +1,185 @@
+// bvh8.cuh — the 8-wide compressed BVH: node layout and per-ray traversal.
+//
+// Replaces the opaque Embree BVH built by rtcCommitScene (src/objects/model.cpp:92-94) and the
+// rtcIntersect1 query (src/objects/model.cpp:27). B200 has no RT cores; this is a software BVH laid
+// out for 16-byte vector loads from L2/HBM:
+//
+//   node  = 80 bytes = five uint4 loads:
+//     n0: origin.xyz (f32) | ex,ey,ez (biased power-of-two exponents) , imask (bit s: slot s is an inner node)
+//     n1: child_base (index of first inner child) | tri_base (index of first leaf triangle) | meta[8]
+//     n2: qlo.x[8] | qlo.y[8]        8-bit child boxes on the grid origin + q * 2^(e-127)
+//     n3: qlo.z[8] | qhi.x[8]
+//     n4: qhi.y[8] | qhi.z[8]
+//     meta[s]: 0 = empty; inner: 0x20 | (24+s); leaf: (unary triangle count 1/3/7) << 5 | first-triangle offset (0..23)
+//   tri   = 48 bytes = three float4 loads: (v0, flat prim id) (e1=v1-v0, 0) (e2=v2-v0, 0)
+//
+// Children are assigned to slots at build time so that slot ^ (7 ^ ray octant) orders them front to
+// back; a node's hit children are kept as one 8-byte stack entry (base index, hit bits), following the
+// compressed-wide-BVH scheme of Ylitie, Karras & Laine (HPG 2017) as published; the code is original.
+//
+// The triangle test is Moeller-Trumbore with a fixed operation sequence of single roundings (see
+// tri_test) so that t,u,v are bit-identical to the CPU oracle; ties in t go to the lowest flat
+// primitive id, which makes closest-hit results independent of the tree and of traversal order.
+#pragma once
+#include "platform.cuh"
+#include "vecmath.cuh"
+
+namespace crb
+{
+    constexpr int      BVH8_STACK      = 48;     // entries; the builder rejects deeper trees loudly
+    constexpr int      BVH8_LEAF_TRIS  = 3;      // max triangles per leaf child
+    constexpr uint32_t INVALID_PRIM    = 0xffffffffu;
+    constexpr float    BVH8_BOX_SLACK  = 1.000001f;    // relative loosening of the slab exit distance
+
+    struct Bvh8
+    {
+        const uint4  *nodes;    // 5 per node
+        const float4 *tris;     // 3 per triangle
+        uint32_t      n_nodes;
+        uint32_t      n_tris;
+    };
+
+    struct Hit
+    {
+        float    t, u, v;
+        uint32_t prim;
+    };
+
+    struct TravCounters
+    {
+        unsigned long long nodes = 0, tris = 0;
+    };
+
+    // Moeller-Trumbore; operation sequence is part of the parity contract (oracle.cpp tri_test):
+    //   p = d x e2, det = e1.p, inv = 1/det, s = o - v0, u = (s.p)*inv, q = s x e1, v = (d.q)*inv,
+    //   t = (e2.q)*inv; accept iff 0<=u<=1, v>=0, u+v<=1, tnear < t <= tfar (Embree's convention).
+    __device__ __forceinline__ bool tri_test(V3 v0, V3 e1, V3 e2, V3 o, V3 d, float tnear, float tfar, float &t, float &u, float &v)
+    {
+        const V3    p   = cross(d, e2);
+        const float det = dot(e1, p);
+        if (det == 0.0f) return false;
+        const float inv = __frcp_rn(det);
+        const V3    s   = o - v0;
+        u               = __fmul_rn(dot(s, p), inv);
+        if (!(u >= 0.0f && u <= 1.0f)) return false;
+        const V3 q = cross(s, e1);
+        v          = __fmul_rn(dot(d, q), inv);
+        if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
+        t = __fmul_rn(dot(e2, q), inv);
+        return t > tnear && t <= tfar;
+    }
+
+    __device__ __forceinline__ float safe_rcp(float d)
+    {
+        const float tiny = 1e-20f;
+        return 1.0f / (fabsf(d) > tiny ? d : copysignf(tiny, d));
+    }
+
+    __device__ __forceinline__ unsigned byte_of(unsigned w, int i) { return (w >> (8 * i)) & 0xffu; }
+
+    // Intersects the ray with the 8 child boxes of one node. Returns the hit bits: bits 24..31 = inner
+    // children at their traversal priority, bits 0..23 = leaf triangles (relative to tri_base).
+    __device__ __forceinline__ unsigned node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, V3 o, V3 idir,
+                                                  unsigned octinv, float tmin, float tmax)
+    {
+        const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+        const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
+                    sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+        const unsigned imask = n0.w >> 24;
+        const float    ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
+        const float    bx = (px - o.x) * idir.x, by = (py - o.y) * idir.y, bz = (pz - o.z) * idir.z;
+        const bool     nx = idir.x < 0.0f, ny = idir.y < 0.0f, nz = idir.z < 0.0f;
+        unsigned       hits = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+        {
+            const unsigned meta4 = half ? n1.w : n1.z;
+            const unsigned lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+            const unsigned hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+            const unsigned nearx = nx ? hix : lox, farx = nx ? lox : hix;
+            const unsigned neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+            const unsigned nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                const unsigned meta = byte_of(meta4, j);
+                const float    t0x = fmaf(float(byte_of(nearx, j)), ax, bx), t1x = fmaf(float(byte_of(farx, j)), ax, bx);
+                const float    t0y = fmaf(float(byte_of(neary, j)), ay, by), t1y = fmaf(float(byte_of(fary, j)), ay, by);
+                const float    t0z = fmaf(float(byte_of(nearz, j)), az, bz), t1z = fmaf(float(byte_of(farz, j)), az, bz);
+                const float    tn  = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+                const float    tf  = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+                if (meta != 0 && tn <= tf * BVH8_BOX_SLACK)
+                {
+                    const int slot = half * 4 + j;
+                    if ((imask >> slot) & 1u)
+                        hits |= 1u << (24 + (slot ^ octinv));
+                    else
+                        hits |= (meta >> 5) << (meta & 31u);
+                }
+            }
+        }
+        return hits;
+    }
+
+    // Closest hit (ANY=false) or any hit (ANY=true) along o + t*d, t in (tmin, tmax].
+    template<bool ANY, bool COUNT>
+    __device__ __forceinline__ Hit traverse(const Bvh8 &bvh, V3 o, V3 d, float tmin, float tmax, TravCounters *ctr)
+    {
+        Hit best { tmax, 0.0f, 0.0f, INVALID_PRIM };
+        if (bvh.n_nodes == 0)
+        {
+            best.t = __int_as_float(0x7f800000);
+            return best;
+        }
+        const V3       idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+        const unsigned oct    = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+        const unsigned octinv = 7u ^ oct;
+
+        uint2 stack[BVH8_STACK];
+        int   sp = 0;
+        // node group: x = base node index, y = hit bits (24..31) | imask (0..7). The root is entered as
+        // the single hit child of a pseudo group with base 0 and an empty imask (relative index 0).
+        uint2 group = make_uint2(0u, 0x80000000u);
+
+        for (;;)
+        {
+            // pop the front-most unvisited inner child of the current group
+            const int bit = 31 - __clz(int(group.y & 0xff000000u));
+            group.y &= ~(1u << bit);
+            if (group.y & 0xff000000u) stack[sp++] = group;
+            const unsigned slot       = unsigned(bit - 24) ^ octinv;
+            const unsigned node_index = group.x + __popc(group.y & 0xffu & ((1u << slot) - 1u));
+
+            const uint4 *np = bvh.nodes + size_t(node_index) * 5;
+            const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) ctr->nodes++;
+            const unsigned h = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, best.t);
+            group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
+            uint2 tgroup     = make_uint2(n1.y, h & 0x00ffffffu);
+
+            while (tgroup.y)
+            {
+                const int i = __ffs(int(tgroup.y)) - 1;
+                tgroup.y &= tgroup.y - 1;
+                const float4 *tp = bvh.tris + size_t(tgroup.x + unsigned(i)) * 3;
+                const float4  a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) ctr->tris++;
+                float t, u, v;
+                if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, best.t, t, u, v))
+                {
+                    const unsigned prim = __float_as_uint(a.w);
+                    if (ANY) return Hit { t, u, v, prim };
+                    if (t < best.t || prim < best.prim) best = Hit { t, u, v, prim };
+                }
+            }
+
+            if ((group.y & 0xff000000u) == 0)
+            {
+                if (sp == 0) break;
+                group = stack[--sp];
+            }
+        }
+        if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
+        return best;
+    }
+}    // namespace crb

@@ -1,0 +1,526 @@
+// bvh_build.cu — device-side BVH build for sm_100a.
+//
+// Replaces rtcCommitGeometry/rtcAttachGeometry/rtcCommitScene (src/objects/model.cpp:92-94), which in
+// the reference is Embree's CPU binned-SAH builder. Pipeline, all on the device:
+//   K1  k_prim_bounds  per-triangle AABBs + centroid bounds (warp-reduced ordered-int atomics)
+//       k_morton       63-bit Morton keys of the centroids; radix sort of (key, prim) pairs
+//   K2  k_hierarchy    LBVH topology from sorted keys (Karras 2012, one thread per inner node)
+//       k_refit        bottom-up AABBs + subtree SAH cost with per-node arrival counters
+//   K3  k_treelet      SAH treelet restructuring (Karras & Aila 2013, 7-leaf treelets, exact DP)
+//   K4  k_collapse     level-synchronous collapse of the binary tree into 8-wide compressed nodes:
+//                      greedy surface-area expansion to 8 children, leaves of <= 3 triangles,
+//                      conservative 8-bit child-box quantisation (in double), octant slot assignment,
+//                      triangles re-packed as (v0,e1,e2,prim) in node order.
+// The published algorithms are followed as described in their papers; the code is original.
+#include "bvh_build.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <vector>
+
+#ifndef CRB_EMU
+#include <cub/device/device_radix_sort.cuh>
+#endif
+
+namespace crb
+{
+    namespace
+    {
+        // ---- ordered-int encoding so float min/max can use integer atomics
+        __device__ __forceinline__ int   f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+        __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+        struct BinTree
+        {
+            // inner node i in [0, n-1); leaf j in [0, n) is referenced as ~j (negative)
+            int    *left, *right;          // children refs
+            int    *parent;                // parent of inner node (-1 for root)
+            int    *leaf_parent;           // parent of leaf (sorted position)
+            int    *first, *last;          // sorted-position range covered by inner node
+            float4 *lo, *hi;               // inner node AABB (w of lo = subtree SAH cost, w of hi = area)
+            int    *flags;                 // arrival counters
+        };
+
+        __global__ void k_prim_bounds(const float *__restrict__ wv, uint32_t n, float4 *__restrict__ plo, float4 *__restrict__ phi, int *bounds)
+        {
+            const uint32_t i   = blockIdx.x * blockDim.x + threadIdx.x;
+            const float    big = 3.0e38f;
+            float          cx0 = big, cy0 = big, cz0 = big, cx1 = -big, cy1 = -big, cz1 = -big;
+            if (i < n)
+            {
+                const float *v = wv + size_t(i) * 9;
+                const float  lx = fminf(v[0], fminf(v[3], v[6])), ly = fminf(v[1], fminf(v[4], v[7])), lz = fminf(v[2], fminf(v[5], v[8]));
+                const float  hx = fmaxf(v[0], fmaxf(v[3], v[6])), hy = fmaxf(v[1], fmaxf(v[4], v[7])), hz = fmaxf(v[2], fmaxf(v[5], v[8]));
+                plo[i]          = make_float4(lx, ly, lz, 0.f);
+                phi[i]          = make_float4(hx, hy, hz, 0.f);
+                cx0 = cx1 = 0.5f * (lx + hx), cy0 = cy1 = 0.5f * (ly + hy), cz0 = cz1 = 0.5f * (lz + hz);
+            }
+#pragma unroll
+            for (int o = CRB_WARP / 2; o > 0; o >>= 1)
+            {
+                cx0 = fminf(cx0, __shfl_xor_sync(0xffffffffu, cx0, o)), cy0 = fminf(cy0, __shfl_xor_sync(0xffffffffu, cy0, o));
+                cz0 = fminf(cz0, __shfl_xor_sync(0xffffffffu, cz0, o)), cx1 = fmaxf(cx1, __shfl_xor_sync(0xffffffffu, cx1, o));
+                cy1 = fmaxf(cy1, __shfl_xor_sync(0xffffffffu, cy1, o)), cz1 = fmaxf(cz1, __shfl_xor_sync(0xffffffffu, cz1, o));
+            }
+            if (crb_lane_id() == 0 && cx0 <= cx1)
+            {
+                atomicMin(bounds + 0, f2ord(cx0)), atomicMin(bounds + 1, f2ord(cy0)), atomicMin(bounds + 2, f2ord(cz0));
+                atomicMax(bounds + 3, f2ord(cx1)), atomicMax(bounds + 4, f2ord(cy1)), atomicMax(bounds + 5, f2ord(cz1));
+            }
+        }
+
+        __device__ __forceinline__ unsigned long long spread21(unsigned long long x)
+        {
+            x &= 0x1fffffull;
+            x = (x | (x << 32)) & 0x1f00000000ffffull;
+            x = (x | (x << 16)) & 0x1f0000ff0000ffull;
+            x = (x | (x << 8)) & 0x100f00f00f00f00full;
+            x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+            x = (x | (x << 2)) & 0x1249249249249249ull;
+            return x;
+        }
+
+        __global__ void k_morton(const float4 *__restrict__ plo, const float4 *__restrict__ phi, uint32_t n, const int *__restrict__ bounds,
+                                 unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            const float  x0 = ord2f(bounds[0]), y0 = ord2f(bounds[1]), z0 = ord2f(bounds[2]);
+            const float  ex = ord2f(bounds[3]) - x0, ey = ord2f(bounds[4]) - y0, ez = ord2f(bounds[5]) - z0;
+            const float4 a = plo[i], b = phi[i];
+            const float  cx = 0.5f * (a.x + b.x), cy = 0.5f * (a.y + b.y), cz = 0.5f * (a.z + b.z);
+            const float  k  = 2097152.0f;    // 2^21
+            const float  fx = ex > 0.f ? (cx - x0) / ex * k : 0.f, fy = ey > 0.f ? (cy - y0) / ey * k : 0.f, fz = ez > 0.f ? (cz - z0) / ez * k : 0.f;
+            const unsigned long long qx = (unsigned long long) fminf(fmaxf(fx, 0.f), k - 1.f), qy = (unsigned long long) fminf(fmaxf(fy, 0.f), k - 1.f),
+                                     qz = (unsigned long long) fminf(fmaxf(fz, 0.f), k - 1.f);
+            keys[i] = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
+            vals[i] = i;
+        }
+
+        // common-prefix length of sorted keys i and j, ties broken by position (Karras 2012 §4)
+        __device__ __forceinline__ int delta(const unsigned long long *__restrict__ keys, int n, int i, int j)
+        {
+            if (j < 0 || j >= n) return -1;
+            const unsigned long long a = keys[i], b = keys[j];
+            if (a == b) return 64 + __clz(i ^ j);
+            return __clzll((long long) (a ^ b));
+        }
+
+        __global__ void k_hierarchy(const unsigned long long *__restrict__ keys, int n, BinTree t)
+        {
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n - 1) return;
+            const int d    = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+            const int dmin = delta(keys, n, i, i - d);
+            int       lmax = 2;
+            while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+            int l = 0;
+            for (int s = lmax / 2; s >= 1; s /= 2)
+                if (delta(keys, n, i, i + (l + s) * d) > dmin) l += s;
+            const int j     = i + l * d;
+            const int dnode = delta(keys, n, i, j);
+            int       s     = 0;
+            int       step  = l;
+            do {
+                step = (step + 1) >> 1;
+                if (delta(keys, n, i, i + (s + step) * d) > dnode) s += step;
+            } while (step > 1);
+            const int gamma = i + s * d + (d < 0 ? -1 : 0);
+            const int lo = i < j ? i : j, hi = i < j ? j : i;
+            const int lref = (lo == gamma) ? ~gamma : gamma;
+            const int rref = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+            t.left[i] = lref, t.right[i] = rref;
+            t.first[i] = lo, t.last[i] = hi;
+            if (lref < 0) t.leaf_parent[~lref] = i; else t.parent[lref] = i;
+            if (rref < 0) t.leaf_parent[~rref] = i; else t.parent[rref] = i;
+            if (i == 0) t.parent[0] = -1;
+        }
+
+        __device__ __forceinline__ float box_area(float4 lo, float4 hi)
+        {
+            const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+            return 2.0f * (ex * ey + ey * ez + ez * ex);
+        }
+
+        constexpr float SAH_CI = 1.2f;    // cost of an inner node relative to a triangle test (Karras & Aila 2013)
+        constexpr float SAH_CT = 1.0f;
+
+        __device__ __forceinline__ void child_box(const BinTree &t, const float4 *plo, const float4 *phi, const uint32_t *vals, int ref, float4 &lo,
+                                                  float4 &hi, float &cost)
+        {
+            if (ref < 0)
+            {
+                const uint32_t p = vals[~ref];
+                lo = plo[p], hi = phi[p];
+                cost = SAH_CT * box_area(lo, hi);
+            }
+            else
+            {
+                lo = t.lo[ref], hi = t.hi[ref];
+                cost = lo.w;
+            }
+        }
+
+        // one thread per leaf walks up; the second thread to arrive at an inner node computes it
+        __global__ void k_refit(int n, BinTree t, const float4 *__restrict__ plo, const float4 *__restrict__ phi, const uint32_t *__restrict__ vals)
+        {
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            int node = t.leaf_parent[i];
+            while (node >= 0)
+            {
+                __threadfence();
+                if (atomicAdd(t.flags + node, 1) == 0) return;
+                __threadfence();
+                float4 alo, ahi, blo, bhi;
+                float  ca, cb;
+                child_box(t, plo, phi, vals, t.left[node], alo, ahi, ca);
+                child_box(t, plo, phi, vals, t.right[node], blo, bhi, cb);
+                float4 lo   = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+                float4 hi   = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+                const float area = box_area(lo, hi);
+                // SAH cost of the subtree: either an inner node over both children, or (small subtrees)
+                // a flat leaf of all its triangles
+                const int   cnt   = t.last[node] - t.first[node] + 1;
+                float       cost  = SAH_CI * area + ca + cb;
+                const float cleaf = SAH_CT * area * float(cnt);
+                if (cnt <= BVH8_LEAF_TRIS && cleaf < cost) cost = cleaf;
+                lo.w = cost, hi.w = area;
+                t.lo[node] = lo, t.hi[node] = hi;
+                node = t.parent[node];
+            }
+        }
+
+        // ------------------------------------------------------------------ K4 collapse
+        struct CollapseCtx
+        {
+            BinTree         t;
+            const float4   *plo, *phi;
+            const uint32_t *vals;
+            const float    *wv;
+            uint4          *nodes;
+            float4         *tris;
+            uint32_t       *counters;    // [0] nodes allocated, [1] tris allocated, [2] out-queue size
+            float          *sah;         // accumulated wide-tree SAH cost (area-weighted), informational
+            float           root_area;
+        };
+
+        __device__ __forceinline__ int ref_count(const BinTree &t, int ref) { return ref < 0 ? 1 : t.last[ref] - t.first[ref] + 1; }
+        __device__ __forceinline__ int ref_first(const BinTree &t, int ref) { return ref < 0 ? ~ref : t.first[ref]; }
+
+        __global__ void k_collapse(CollapseCtx c, const uint2 *__restrict__ in, uint32_t n_in, uint2 *__restrict__ out)
+        {
+            const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+            if (w >= n_in) return;
+            const int      root = int(in[w].x);
+            const uint32_t self = in[w].y;
+
+            int ch[8];
+            int k = 0;
+            if (root >= 0)
+                ch[0] = c.t.left[root], ch[1] = c.t.right[root], k = 2;
+            else
+                ch[0] = root, k = 1;
+            // greedy expansion: open the inner child with the largest surface area until 8 children
+            while (k < 8)
+            {
+                int   best  = -1;
+                float besta = -1.f;
+                for (int j = 0; j < k; j++)
+                    if (ch[j] >= 0)
+                    {
+                        const float a = c.t.hi[ch[j]].w;
+                        if (a > besta) besta = a, best = j;
+                    }
+                if (best < 0) break;
+                const int r = ch[best];
+                ch[best]    = c.t.left[r];
+                ch[k++]     = c.t.right[r];
+            }
+
+            float4 clo[8], chi[8];
+            float  nlo[3] = { 3e38f, 3e38f, 3e38f }, nhi[3] = { -3e38f, -3e38f, -3e38f };
+            for (int j = 0; j < k; j++)
+            {
+                float cost;
+                child_box(c.t, c.plo, c.phi, c.vals, ch[j], clo[j], chi[j], cost);
+                nlo[0] = fminf(nlo[0], clo[j].x), nlo[1] = fminf(nlo[1], clo[j].y), nlo[2] = fminf(nlo[2], clo[j].z);
+                nhi[0] = fmaxf(nhi[0], chi[j].x), nhi[1] = fmaxf(nhi[1], chi[j].y), nhi[2] = fmaxf(nhi[2], chi[j].z);
+            }
+
+            // slot assignment: child j -> slot s maximising (centroid_j - centroid_node) . sign(s), greedily
+            int  child_in_slot[8];
+            bool slot_used[8], child_done[8];
+            for (int j = 0; j < 8; j++) slot_used[j] = false, child_done[j] = false, child_in_slot[j] = -1;
+            const float ncx = 0.5f * (nlo[0] + nhi[0]), ncy = 0.5f * (nlo[1] + nhi[1]), ncz = 0.5f * (nlo[2] + nhi[2]);
+            for (int round = 0; round < k; round++)
+            {
+                float bestc = -3e38f;
+                int   bj = -1, bs = -1;
+                for (int j = 0; j < k; j++)
+                {
+                    if (child_done[j]) continue;
+                    const float dx = 0.5f * (clo[j].x + chi[j].x) - ncx, dy = 0.5f * (clo[j].y + chi[j].y) - ncy, dz = 0.5f * (clo[j].z + chi[j].z) - ncz;
+                    for (int s = 0; s < 8; s++)
+                    {
+                        if (slot_used[s]) continue;
+                        const float cost = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
+                        if (cost > bestc) bestc = cost, bj = j, bs = s;
+                    }
+                }
+                child_in_slot[bs] = bj, slot_used[bs] = true, child_done[bj] = true;
+            }
+
+            // classify and allocate
+            int n_inner = 0, n_ltris = 0;
+            for (int s = 0; s < 8; s++)
+            {
+                const int j = child_in_slot[s];
+                if (j < 0) continue;
+                const int cnt = ref_count(c.t, ch[j]);
+                if (cnt <= BVH8_LEAF_TRIS) n_ltris += cnt; else n_inner++;
+            }
+            const uint32_t child_base = n_inner ? atomicAdd(c.counters + 0, uint32_t(n_inner)) : 0u;
+            const uint32_t tri_base   = n_ltris ? atomicAdd(c.counters + 1, uint32_t(n_ltris)) : 0u;
+            const uint32_t out_base   = n_inner ? atomicAdd(c.counters + 2, uint32_t(n_inner)) : 0u;
+
+            // quantisation frame (double: the grid must contain every child box exactly-conservatively)
+            unsigned eb[3];
+            double   scale[3];
+            for (int a = 0; a < 3; a++)
+            {
+                const double ext = double(nhi[a]) - double(nlo[a]);
+                int          e   = -126;
+                if (ext > 0.0)
+                {
+                    int x;
+                    frexp(ext / 255.0, &x);    // ext/255 = m * 2^x, m in [0.5,1)  ->  2^x > ext/255
+                    e = x;
+                }
+                int b = e + 127;
+                b     = b < 1 ? 1 : (b > 254 ? 254 : b);
+                eb[a] = unsigned(b);
+                scale[a] = ldexp(1.0, b - 127);
+            }
+
+            unsigned meta[8], qlo[3][8], qhi[3][8];
+            unsigned imask = 0;
+            int      inner_i = 0, tri_off = 0;
+            float    leaf_area_tris = 0.f;
+            for (int s = 0; s < 8; s++)
+            {
+                meta[s] = 0;
+                for (int a = 0; a < 3; a++) qlo[a][s] = 255u, qhi[a][s] = 0u;
+                const int j = child_in_slot[s];
+                if (j < 0) continue;
+                const float lo3[3] = { clo[j].x, clo[j].y, clo[j].z }, hi3[3] = { chi[j].x, chi[j].y, chi[j].z };
+                for (int a = 0; a < 3; a++)
+                {
+                    const double p = double(nlo[a]);
+                    double       q = floor((double(lo3[a]) - p) / scale[a]);
+                    q              = q < 0.0 ? 0.0 : (q > 255.0 ? 255.0 : q);
+                    while (q > 0.0 && p + q * scale[a] > double(lo3[a])) q -= 1.0;
+                    qlo[a][s] = unsigned(q);
+                    double r  = ceil((double(hi3[a]) - p) / scale[a]);
+                    r         = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
+                    while (r < 255.0 && p + r * scale[a] < double(hi3[a])) r += 1.0;
+                    qhi[a][s] = unsigned(r);
+                }
+                const int cnt = ref_count(c.t, ch[j]);
+                if (cnt <= BVH8_LEAF_TRIS)
+                {
+                    meta[s]         = (((1u << cnt) - 1u) << 5) | unsigned(tri_off);
+                    const int first = ref_first(c.t, ch[j]);
+                    for (int q = 0; q < cnt; q++)
+                    {
+                        const uint32_t prim = c.vals[first + q];
+                        const float   *v    = c.wv + size_t(prim) * 9;
+                        float4        *dst  = c.tris + size_t(tri_base + uint32_t(tri_off + q)) * 3;
+                        dst[0]              = make_float4(v[0], v[1], v[2], __uint_as_float(prim));
+                        dst[1]              = make_float4(__fsub_rn(v[3], v[0]), __fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), 0.f);
+                        dst[2]              = make_float4(__fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]), __fsub_rn(v[8], v[2]), 0.f);
+                    }
+                    tri_off += cnt;
+                    leaf_area_tris += box_area(clo[j], chi[j]) * float(cnt);
+                }
+                else
+                {
+                    meta[s] = 0x20u | unsigned(24 + s);
+                    imask |= 1u << s;
+                    out[out_base + uint32_t(inner_i)] = make_uint2(unsigned(ch[j]), child_base + uint32_t(inner_i));
+                    inner_i++;
+                }
+            }
+
+            auto pack4 = [](const unsigned *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+            uint4 *np  = c.nodes + size_t(self) * 5;
+            np[0]      = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+            np[1]      = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+            np[2]      = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+            np[3]      = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+            np[4]      = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+
+            if (c.root_area > 0.f)
+            {
+                const float na = 2.0f * ((nhi[0] - nlo[0]) * (nhi[1] - nlo[1]) + (nhi[1] - nlo[1]) * (nhi[2] - nlo[2]) + (nhi[2] - nlo[2]) * (nhi[0] - nlo[0]));
+                atomicAdd(c.sah, (SAH_CI * na + SAH_CT * leaf_area_tris) / c.root_area);
+            }
+        }
+
+#include "bvh_treelet.inl"
+
+        template<typename T>
+        T *carve(char *&p, size_t count)
+        {
+            T *r = reinterpret_cast<T *>(p);
+            p += (count * sizeof(T) + 255) & ~size_t(255);
+            return r;
+        }
+    }    // namespace
+
+    void build_bvh8(const float *d_wverts, uint32_t n, cudaStream_t stream, const BuildOptions &opt, DBuf<uint4> &nodes, DBuf<float4> &tris,
+                    BuildStats &stats)
+    {
+        stats = BuildStats();
+        if (n > 0x7ffffff0u) throw Error(ERR_BUILD_INDEX, "too many triangles for 32-bit primitive ids");
+#ifdef CRB_EMU
+        auto t0 = std::chrono::steady_clock::now();
+#else
+        cudaEvent_t ev0, ev1;
+        CRB_CUDA_CHECK(cudaEventCreate(&ev0));
+        CRB_CUDA_CHECK(cudaEventCreate(&ev1));
+        CRB_CUDA_CHECK(cudaEventRecord(ev0, stream));
+#endif
+        const size_t max_nodes = size_t(n) / 2 + 8;
+        nodes.alloc(max_nodes * 5);
+        tris.alloc(size_t(n ? n : 1) * 3);
+
+        if (n == 0)
+        {
+            // empty scene: one root with no children
+            std::vector<uint4> root(5, make_uint4(0, 0, 0, 0));
+            root[0] = make_uint4(0, 0, 0, 127u | (127u << 8) | (127u << 16));
+            dev_upload(nodes.p, root.data(), 80, stream);
+            stream_sync(stream);
+            stats.n_nodes = 1, stats.max_depth = 1;
+            return;
+        }
+
+        // ---- scratch
+        const size_t ni = n > 1 ? n - 1 : 1;
+        size_t       bytes = 0;
+        auto         sz    = [&](size_t count, size_t elem) { bytes += (count * elem + 255) & ~size_t(255); };
+        sz(n, 16), sz(n, 16);                 // plo, phi
+        sz(8, 4);                             // bounds
+        sz(n, 8), sz(n, 8), sz(n, 4), sz(n, 4);    // keys x2, vals x2
+        sz(ni, 4), sz(ni, 4), sz(ni, 4), sz(n, 4), sz(ni, 4), sz(ni, 4), sz(ni, 16), sz(ni, 16), sz(ni, 4);    // tree
+        sz(max_nodes, 8), sz(max_nodes, 8);   // collapse queues
+        sz(8, 4);                             // counters + sah
+        DBuf<char> scratch;
+        scratch.alloc(bytes + 4096);
+        char   *p    = scratch.p;
+        float4 *plo  = carve<float4>(p, n), *phi = carve<float4>(p, n);
+        int    *bounds = carve<int>(p, 8);
+        unsigned long long *keys0 = carve<unsigned long long>(p, n), *keys1 = carve<unsigned long long>(p, n);
+        uint32_t *vals0 = carve<uint32_t>(p, n), *vals1 = carve<uint32_t>(p, n);
+        BinTree   t;
+        t.left = carve<int>(p, ni), t.right = carve<int>(p, ni), t.parent = carve<int>(p, ni), t.leaf_parent = carve<int>(p, n);
+        t.first = carve<int>(p, ni), t.last = carve<int>(p, ni);
+        t.lo = carve<float4>(p, ni), t.hi = carve<float4>(p, ni);
+        t.flags      = carve<int>(p, ni);
+        uint2    *q0 = carve<uint2>(p, max_nodes), *q1 = carve<uint2>(p, max_nodes);
+        uint32_t *counters = carve<uint32_t>(p, 8);
+
+        const int      B  = 256;
+        const unsigned gn = (n + B - 1) / B;
+
+        // ---- K1
+        {
+            const int big = 0x7f7fffff;
+            int       init[8] = { big, big, big, ~big, ~big, ~big, 0, 0 };
+            // ordered encoding of +max float is `big`; of -max float is (0xff7fffff ^ 0x7fffffff) = 0x80800000
+            init[3] = init[4] = init[5] = int(0x80800000u);
+            dev_upload(bounds, init, sizeof(init), stream);
+        }
+        CRB_LAUNCH(k_prim_bounds, gn, B, stream, d_wverts, n, plo, phi, bounds);
+        CRB_LAUNCH(k_morton, gn, B, stream, plo, phi, n, bounds, keys0, vals0);
+
+        const unsigned long long *keys = keys1;
+        const uint32_t           *vals = vals1;
+#ifdef CRB_EMU
+        {
+            std::vector<std::pair<unsigned long long, uint32_t>> kv(n);
+            for (uint32_t i = 0; i < n; i++) kv[i] = { keys0[i], vals0[i] };
+            std::stable_sort(kv.begin(), kv.end(), [](auto &a, auto &b) { return a.first < b.first; });
+            for (uint32_t i = 0; i < n; i++) keys1[i] = kv[i].first, vals1[i] = kv[i].second;
+        }
+#else
+        {
+            size_t tmp_bytes = 0;
+            CRB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys0, keys1, vals0, vals1, int(n), 0, 63, stream));
+            DBuf<char> tmp;
+            tmp.alloc(tmp_bytes);
+            CRB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys0, keys1, vals0, vals1, int(n), 0, 63, stream));
+            stream_sync(stream);    // tmp is freed at scope exit
+        }
+#endif
+
+        // ---- K2
+        float root_area = 0.f;
+        int   root_ref  = ~0;    // single triangle: the root reference is leaf 0
+        if (n > 1)
+        {
+            dev_zero(t.flags, ni * sizeof(int), stream);
+            CRB_LAUNCH(k_hierarchy, (unsigned(ni) + B - 1) / B, B, stream, keys, int(n), t);
+            CRB_LAUNCH(k_refit, gn, B, stream, int(n), t, plo, phi, vals);
+            // ---- K3
+            if (opt.treelets && n >= 16) treelet_optimize(t, int(n), plo, phi, vals, stream);
+            float4 hi0;
+            dev_download(&hi0, t.hi, sizeof(float4), stream);
+            root_area = hi0.w;
+            root_ref  = 0;
+        }
+
+        // ---- K4
+        {
+            uint32_t init[8] = { 1, 0, 0, 0, 0, 0, 0, 0 };    // node 0 = root is pre-allocated
+            dev_upload(counters, init, sizeof(init), stream);
+            uint2 first = make_uint2(unsigned(root_ref), 0u);
+            dev_upload(q0, &first, sizeof(first), stream);
+        }
+        CollapseCtx c;
+        c.t = t, c.plo = plo, c.phi = phi, c.vals = vals, c.wv = d_wverts, c.nodes = nodes.p, c.tris = tris.p;
+        c.counters = counters, c.sah = reinterpret_cast<float *>(counters + 4), c.root_area = root_area;
+        uint32_t n_in  = 1;
+        uint32_t depth = 0;
+        uint2   *qin = q0, *qout = q1;
+        while (n_in)
+        {
+            depth++;
+            CRB_LAUNCH(k_collapse, (n_in + 127) / 128, 128, stream, c, qin, n_in, qout);
+            uint32_t cnt[3];
+            dev_download(cnt, counters, sizeof(cnt), stream);
+            if (cnt[0] > max_nodes) throw Error(ERR_GENERIC, "internal: wide node pool overflow");
+            n_in = cnt[2];
+            const uint32_t zero = 0;
+            dev_upload(counters + 2, &zero, 4, stream);
+            std::swap(qin, qout);
+        }
+        uint32_t fin[5];
+        dev_download(fin, counters, sizeof(fin), stream);
+        stats.n_nodes = fin[0], stats.n_tris = fin[1], stats.max_depth = depth;
+        memcpy(&stats.sah_cost, &fin[4], 4);
+        if (stats.n_tris != n) throw Error(ERR_GENERIC, "internal: triangle count mismatch after collapse");
+        if (depth > uint32_t(BVH8_STACK)) throw Error(ERR_BVH_DEPTH, "BVH depth " + std::to_string(depth) + " exceeds the traversal stack");
+#ifdef CRB_EMU
+        stats.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+#else
+        CRB_CUDA_CHECK(cudaEventRecord(ev1, stream));
+        CRB_CUDA_CHECK(cudaEventSynchronize(ev1));
+        float ms = 0;
+        CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+        stats.build_ms = ms;
+        cudaEventDestroy(ev0), cudaEventDestroy(ev1);
+#endif
+    }
+}    // namespace crb

@@ -1,0 +1,27 @@
+// bvh_build.cuh — interface of the device-side BVH builder (the rtcCommitScene replacement,
+// src/objects/model.cpp:92-94).
+#pragma once
+#include "platform.cuh"
+#include "bvh8.cuh"
+
+namespace crb
+{
+    struct BuildStats
+    {
+        double   build_ms  = 0;
+        uint32_t n_nodes   = 0;
+        uint32_t n_tris    = 0;
+        uint32_t max_depth = 0;
+        float    sah_cost  = 0;
+    };
+
+    struct BuildOptions
+    {
+        bool treelets = true;    // SAH treelet restructuring passes on the binary tree before collapse
+    };
+
+    // wverts: device pointer, 9 floats per triangle (world space), n triangles.
+    // Produces the node and triangle arrays of the 8-wide BVH. Throws crb::Error on failure.
+    void build_bvh8(const float *d_wverts, uint32_t n, cudaStream_t stream, const BuildOptions &opt, DBuf<uint4> &nodes, DBuf<float4> &tris,
+                    BuildStats &stats);
+}    // namespace crb

@@ -1,0 +1,726 @@
+// render.cu — wavefront path tracer (K6-K9).
+//
+// Replaces cr::renderer's hot loop: the management thread that issues one pass at a time
+// (src/render/renderer.cpp:116-144), the per-scanline tasks (:240-256), _sample_pixel (:258-384) and
+// process_hit (:21-102). Instead of "one CPU task per scanline, one sample per pixel per pass", a batch
+// of (pixels x samples) paths is resident in HBM as a structure of arrays and every bounce is a
+// sequence of persistent kernels fed by warp-aggregated atomic queues:
+//
+//   k_raygen      camera::get_ray + jitter (camera.cpp:14-39, renderer.cpp:260-263)            K6
+//   per bounce i:
+//     k_trace     closest hit for every active path (scene::cast_ray semantics) and a material
+//                 sort: each hit is pushed to the queue of its shade type (miss/metal/smooth/glass)
+//     k_shade     process_hit + the body of the bounce loop (renderer.cpp:277-313) + sun-NEE sample
+//                 generation (:316-329); pushes survivors to the next queue, shadow rays to theirs  K7
+//     k_shadow    sun visibility (renderer.cpp:330-353): any-hit, or the reference's closest-hit
+//                 march when alpha cut-outs exist; connects the contribution                        K8
+//     k_advance   swaps queue counters, accumulates ray statistics
+//   k_accumulate  float4 accumulation buffer += per-sample radiance in sample order, AOVs, resolve
+//                 pow(clamp(sum/n,0,1),1/2.2) (renderer.cpp:358-383)                                K9
+//
+// All shading arithmetic is single-rounding float in the reference's operation order (vecmath.cuh);
+// this file is compiled with -fmad=false. Sampler dimensions: see rnd() below and DESIGN.md.
+#include "render.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace crb
+{
+    namespace
+    {
+        constexpr float TAU_F     = 6.28318530717f;           // src/util/numbers.h:17
+        constexpr float INV_PI_F  = 1.0f / 3.14159265359f;    // :22
+        constexpr float INV_TAU_F = 1.0f / 6.28318530717f;    // :24
+
+        // ---- counter-based sampler (replaces the thread_local mt19937 of renderer.cpp:6-11, which is
+        // default-seeded per worker thread and not reproducible). key = f(seed, pixel, sample);
+        // u(dim) = top 24 bits of mix(key + dim*golden). dims: 0,1 jitter; 2+4i+{0,1} scatter of bounce
+        // i; 2+4i+{2,3} sun cone sample of bounce i.
+        __device__ __forceinline__ uint32_t mix32(uint32_t x)
+        {
+            x ^= x >> 16;
+            x *= 0x7feb352du;
+            x ^= x >> 15;
+            x *= 0x846ca68bu;
+            x ^= x >> 16;
+            return x;
+        }
+        __device__ __forceinline__ uint32_t path_key(uint32_t seed, uint32_t pixel, uint32_t sample)
+        {
+            return mix32(mix32(mix32(seed + 0x9e3779b9u) ^ pixel) ^ sample);
+        }
+        __device__ __forceinline__ float rnd(uint32_t key, uint32_t dim) { return float(mix32(key + dim * 0x9e3779b9u) >> 8) * (1.0f / 16777216.0f); }
+
+        __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
+
+        // ---- warp-aggregated queue push: one atomic per warp per queue
+        __device__ __forceinline__ uint32_t warp_push(uint32_t *counter, bool pred)
+        {
+            const unsigned mask = __ballot_sync(0xffffffffu, pred);
+            if (mask == 0) return 0;
+            const int leader = __ffs(int(mask)) - 1;
+            uint32_t  base   = 0;
+            if (int(crb_lane_id()) == leader) base = atomicAdd(counter, uint32_t(__popc(mask)));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            return base + uint32_t(__popc(mask & ((1u << crb_lane_id()) - 1u)));
+        }
+        // persistent work fetch: a warp takes CRB_WARP consecutive items at a time
+        __device__ __forceinline__ uint32_t warp_fetch(uint32_t *cursor)
+        {
+            uint32_t base = 0;
+            if (crb_lane_id() == 0) base = atomicAdd(cursor, uint32_t(CRB_WARP));
+            return __shfl_sync(0xffffffffu, base, 0);
+        }
+
+        // ---- cr::image::get_uv, src/objects/image.h:104-121. static_cast<uint64_t>(float) of a negative
+        // value goes through the signed conversion on x86-64 (what the reference's build computes).
+        __device__ __forceinline__ unsigned long long to_u64(float f)
+        {
+            if (!(f == f)) return 0x8000000000000000ull;
+            if (f >= 9223372036854775808.0f) return (unsigned long long) f;
+            return (unsigned long long) (long long) f;
+        }
+        __device__ __forceinline__ float4 image_get_uv(const float4 *px, uint32_t w, uint32_t h, float u, float v)
+        {
+            const unsigned long long x = to_u64(u * float(w)) % w;
+            const unsigned long long y = to_u64(v * float(h)) % h;
+            return __ldg(px + (x + y * w));
+        }
+
+        __device__ __forceinline__ uint32_t src_tri(const DScene &sc, uint32_t flat) { return sc.flat_src ? __ldg(sc.flat_src + flat) : flat; }
+
+        __device__ __forceinline__ uint32_t flipped_index(const RenderParams &rp, uint32_t x, uint32_t y)
+        {
+            return (rp.w - 1 - x) + (rp.h - 1 - y) * rp.w;    // renderer.cpp:358-362
+        }
+
+        // ------------------------------------------------------------------ K6 ray generation
+        __global__ void __launch_bounds__(256) k_raygen(DScene sc, RenderParams rp, PathState ps)
+        {
+            const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+            if (slot >= rp.npix * rp.batch) return;
+            const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
+            const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+            const uint32_t sample = rp.first_sample + s;
+            const uint32_t key    = path_key(rp.seed, x + y * rp.w, sample);
+            const float    fx = (float(x) + rnd(key, 0)) / float(rp.w), fy = (float(y) + rnd(key, 1)) / float(rp.h);    // renderer.cpp:260-263
+            const DCamera &c = sc.cam;
+            V3             o, d;
+            if (c.mode == 0)
+            {
+                // camera.cpp:18-27
+                const float u = (2.0f * fx - 1.0f) * c.aspect;
+                const float v = 2.0f * fy - 1.0f;
+                const float w = c.w;
+                float       r[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) r[k] = (c.m[0][k] * u + c.m[1][k] * v) + (c.m[2][k] * w + c.trans[k] * 0.0f);
+                o = v3(c.position[0], c.position[1], c.position[2]);
+                d = normalize(v3(r[0], r[1], r[2]));
+            }
+            else
+            {
+                // camera.cpp:28-37
+                const float u = 2.0f * fx - 1.0f, v = 2.0f * fy - 1.0f;
+                const float su = c.scale * u, sv = c.scale * v;
+                float       r[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) r[k] = (c.m[0][k] * su + c.m[1][k] * sv) + (c.m[2][k] * 0.0f + c.trans[k] * 1.0f);
+                o = v3(r[0], r[1], r[2]);
+                d = normalize(v3(c.m[2][0], c.m[2][1], c.m[2][2]));
+            }
+            ps.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.f);
+            ps.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+            ps.thr[slot]   = make_float4(1.f, 1.f, 1.f, 0.f);
+            ps.rad[slot]   = make_float4(0.f, 0.f, 0.f, 0.f);
+            ps.q_in[slot]  = slot;
+            if (sample == rp.aov_sample)
+            {
+                // defaults of renderer.cpp:265-269 pushed through :367-369
+                const uint32_t fi = flipped_index(rp, x, y);
+                rp.albedo[fi]     = make_float4(0.f, 0.f, 0.f, 1.f);
+                rp.normal[fi]     = make_float4(.5f, .5f, .5f, 1.f);
+                rp.depth[fi]      = make_float4(0.f, 0.f, 0.f, 1.f);
+            }
+        }
+
+        // ------------------------------------------------------------------ trace + material sort
+        template<bool COUNT>
+        __global__ void __launch_bounds__(256) k_trace(DScene sc, PathState ps)
+        {
+            const uint32_t n = ps.counters[CTR_IN];
+            TravCounters   tc;
+            for (;;)
+            {
+                const uint32_t base = warp_fetch(ps.counters + CTR_CUR_TRACE);
+                if (base >= n) break;
+                const uint32_t idx = base + crb_lane_id();
+                int            cls  = -1;
+                uint32_t       slot = 0;
+                if (idx < n)
+                {
+                    slot           = ps.q_in[idx];
+                    const float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
+                    // model.cpp:107-112: the query direction is normalised; tnear/tfar of model.cpp:21-22
+                    const V3  dn = normalize(v3(d.x, d.y, d.z));
+                    const Hit h  = traverse<false, COUNT>(sc.bvh, v3(o.x, o.y, o.z), dn, 0.00001f, inf_f(), &tc);
+                    ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                    if (h.prim == INVALID_PRIM)
+                        cls = 0;
+                    else
+                    {
+                        const uint32_t mat = __float_as_uint(__ldg(sc.shade_tri + src_tri(sc, h.prim)).w);
+                        cls                = 1 + int(sc.materials[mat].shade_type);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                {
+                    const uint32_t at = warp_push(ps.counters + CTR_CLASS0 + c, cls == c);
+                    if (cls == c) ps.q_class[c][at] = slot;
+                }
+            }
+            if (COUNT)
+            {
+                atomicAdd(ps.stats + ST_NODES, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS, tc.tris);
+            }
+        }
+
+        // ------------------------------------------------------------------ shading
+        struct Surface
+        {
+            V3       normal;    // object-space unit geometric normal, not face-forwarded (model.cpp:35)
+            V3       point;     // intersection_point (model.cpp:33,116)
+            float    distance;  // re-measured |point - origin| (model.cpp:119-120)
+            uint32_t mat;
+            float    uvx, uvy;
+        };
+
+        __device__ __forceinline__ Surface surface_at(const DScene &sc, V3 o, V3 dn, float4 hit)
+        {
+            Surface        s;
+            const uint32_t src = src_tri(sc, __float_as_uint(hit.w));
+            const float4   st  = __ldg(sc.shade_tri + src);
+            s.normal           = v3(st.x, st.y, st.z);
+            s.mat              = __float_as_uint(st.w);
+            s.point            = o + dn * hit.x;            // ray.at(tfar), ray.cpp:13-16
+            s.distance         = length(s.point - o);       // glm::distance
+            s.uvx = s.uvy = 0.f;
+            if (sc.obj_uvs)
+            {
+                // rtcInterpolate0 (model.cpp:39-47): (1-u-v)*t0 + u*t1 + v*t2
+                const float *t = sc.obj_uvs + size_t(src) * 6;
+                const float  w = 1.0f - hit.y - hit.z;
+                s.uvx          = (w * t[0] + hit.y * t[2]) + hit.z * t[4];
+                s.uvy          = (w * t[1] + hit.y * t[3]) + hit.z * t[5];
+            }
+            return s;
+        }
+
+        __device__ __forceinline__ float4 surface_colour(const DScene &sc, const DMaterial &m, const Surface &s)
+        {
+            if (m.tex >= 0)
+            {
+                const DTexture t = sc.textures[m.tex];
+                return image_get_uv(sc.texels + t.offset, t.w, t.h, s.uvx, s.uvy);    // renderer.cpp:30-33
+            }
+            return make_float4(m.colour[0], m.colour[1], m.colour[2], m.colour[3]);
+        }
+
+        // src/util/sampling.h:156-166
+        __device__ __forceinline__ V3 sample_sphere(float ux, float uy)
+        {
+            const float cos_theta = 2.0f * ux - 1.0f;
+            const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+            const float phi       = TAU_F * uy;
+            const float sin_phi = sinf(phi), cos_phi = cosf(phi);
+            return v3(sin_theta * cos_phi, cos_theta, sin_theta * sin_phi);
+        }
+        // src/util/sampling.h:35-42 with 1-cos(theta_max) hoisted to the host
+        __device__ __forceinline__ V3 map_to_solid_angle(float ux, float uy, float one_minus_cos)
+        {
+            const float phi       = TAU_F * ux;
+            const float cos_theta = 1.0f - uy * one_minus_cos;
+            const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+            return v3(cosf(phi) * sin_theta, cos_theta, sinf(phi) * sin_theta);
+        }
+
+        __global__ void __launch_bounds__(256) k_shade(DScene sc, RenderParams rp, PathState ps)
+        {
+            const uint32_t c0 = ps.counters[CTR_CLASS0], c1 = c0 + ps.counters[CTR_CLASS0 + 1], c2 = c1 + ps.counters[CTR_CLASS0 + 2],
+                           n = c2 + ps.counters[CTR_CLASS0 + 3];
+            const uint32_t i = rp.bounce;
+            for (;;)
+            {
+                const uint32_t base = warp_fetch(ps.counters + CTR_CUR_SHADE);
+                if (base >= n) break;
+                const uint32_t idx      = base + crb_lane_id();
+                bool           survive  = false, want_shadow = false;
+                uint32_t       slot     = 0;
+                ShadowRay      sr;
+                if (idx < n)
+                {
+                    const int cls = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
+                    slot          = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
+                    const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                    const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
+                    const float4 t4 = ps.thr[slot];
+                    V3           thr = v3(t4.x, t4.y, t4.z);
+                    const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
+                    const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+                    const uint32_t sample = rp.first_sample + s;
+                    const bool     aov    = (i == 0) && (sample == rp.aov_sample);
+
+                    if (cls == 0)
+                    {
+                        // renderer.cpp:277-289
+                        V3 ms = v3(0.f, 0.f, 0.f);
+                        if (sc.skybox)
+                        {
+                            const float mu = 0.5f + atan2f(d.z, d.x) * INV_TAU_F;
+                            const float mv = 0.5f - asinf(d.y) * INV_PI_F;
+                            const float4 c = image_get_uv(sc.skybox, sc.sky_w, sc.sky_h, mu + sc.sky_rot[0], mv + sc.sky_rot[1]);    // scene.cpp:67-77
+                            ms             = v3(c.x, c.y, c.z);
+                        }
+                        if (aov) rp.albedo[flipped_index(rp, x, y)] = make_float4(ms.x, ms.y, ms.z, 1.f);
+                        const float4 r4 = ps.rad[slot];
+                        const V3     r  = v3(r4.x, r4.y, r4.z) + thr * ms;
+                        ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                    }
+                    else
+                    {
+                        const V3         dn  = normalize(d);
+                        const Surface    sf  = surface_at(sc, o, dn, ps.hit[slot]);
+                        const DMaterial  mat = sc.materials[sf.mat];
+                        const float4     col = surface_colour(sc, mat, sf);
+                        if (col.w == 0.0f)
+                        {
+                            // alpha cut-out: renderer.cpp:294-301 (steps 0.1 along the un-normalised direction)
+                            const V3 p     = sf.point + d * 0.1f;
+                            ps.ray_o[slot] = make_float4(p.x, p.y, p.z, 0.f);
+                            survive        = true;
+                        }
+                        else
+                        {
+                            V3 albedo = v3(col.x, col.y, col.z);
+                            V3 no, nd;
+                            if (mat.shade_type == CRB_GLASS)
+                            {
+                                // renderer.cpp:47-77
+                                V3       out_normal = sf.normal;
+                                const V3 reflected  = reflect(d, sf.normal);
+                                float    ni_over_nt = 1.0f / mat.ior;
+                                if (dot(d, sf.normal) > 0) out_normal = -sf.normal, ni_over_nt = mat.ior;
+                                const V3    uv   = dn;
+                                const float dt   = dot(uv, out_normal);
+                                const float disc = 1.0f - ni_over_nt * ni_over_nt * (1.0f - dt * dt);
+                                no               = sf.point + out_normal * -0.0001f;
+                                if (disc > 0)
+                                    nd = ni_over_nt * (uv - out_normal * dt) - out_normal * sqrtf(disc);
+                                else
+                                    nd = reflected;
+                            }
+                            else if (mat.shade_type == CRB_METAL)
+                            {
+                                // renderer.cpp:78-91 (the hemp_cos draw is computed and discarded there)
+                                no     = sf.point + sf.normal * 0.0001f;
+                                nd     = reflect(d, sf.normal);
+                                albedo = albedo * mat.reflectiveness;
+                            }
+                            else
+                            {
+                                // renderer.cpp:92-98, sampling.h:168-172
+                                const uint32_t key = path_key(rp.seed, x + y * rp.w, sample);
+                                const V3       h   = sf.normal + sample_sphere(rnd(key, 2 + 4 * i), rnd(key, 2 + 4 * i + 1));
+                                no                 = sf.point + sf.normal * 0.0001f;
+                                nd                 = normalize(h);
+                            }
+                            if (aov)
+                            {
+                                // renderer.cpp:303-308,367-369
+                                const uint32_t fi = flipped_index(rp, x, y);
+                                rp.albedo[fi]     = make_float4(albedo.x, albedo.y, albedo.z, 1.f);
+                                const V3 nn       = sf.normal * .5f + v3(.5f, .5f, .5f);
+                                rp.normal[fi]     = make_float4(nn.x, nn.y, nn.z, 1.f);
+                                const float dd    = fminf(sf.distance, 200.0f) / 200.f;
+                                rp.depth[fi]      = make_float4(dd, dd, dd, 1.f);
+                            }
+                            // renderer.cpp:310-312
+                            thr             = thr * albedo;
+                            const float4 r4 = ps.rad[slot];
+                            const V3     r  = v3(r4.x, r4.y, r4.z) + thr * mat.emission;
+                            ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                            ps.thr[slot]    = make_float4(thr.x, thr.y, thr.z, 0.f);
+                            ps.ray_o[slot]  = make_float4(no.x, no.y, no.z, 0.f);
+                            ps.ray_d[slot]  = make_float4(nd.x, nd.y, nd.z, 0.f);
+                            survive         = true;
+
+                            if (sc.sun.enabled)
+                            {
+                                // renderer.cpp:316-329,348-353; sampling.h:53-57,72-80
+                                const uint32_t key = path_key(rp.seed, x + y * rp.w, sample);
+                                const V3       so  = sf.point + sf.normal * 0.001f;
+                                const V3       l   = map_to_solid_angle(rnd(key, 2 + 4 * i + 2), rnd(key, 2 + 4 * i + 3), sc.sun.one_minus_cos);
+                                const float   *T   = sc.sun.transform;
+                                const V3       dir = (v3(T[0], T[1], T[2]) * l.x + v3(T[3], T[4], T[5]) * l.y) + v3(T[6], T[7], T[8]) * l.z;
+                                const float    cosine    = clampf(dot(sf.normal, dir), 0.0f, 1.0f);
+                                const float    sun_angle = acosf(dot(dir, -v3(sc.sun.dir[0], sc.sun.dir[1], sc.sun.dir[2])));
+                                const V3       sky = (sun_angle < sc.sun.size) ? v3(sc.sun.colour[0], sc.sun.colour[1], sc.sun.colour[2]) * sc.sun.intensity
+                                                                               : v3(0.f, 0.f, 0.f);
+                                const V3       contrib = thr * v3(col.x, col.y, col.z) * cosine * sky / sc.sun.pdf;
+                                if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f)
+                                {
+                                    want_shadow = true;
+                                    sr.o        = make_float4(so.x, so.y, so.z, __uint_as_float(slot));
+                                    sr.d        = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                    sr.c        = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                                }
+                            }
+                        }
+                    }
+                }
+                const uint32_t at = warp_push(ps.counters + CTR_NEXT, survive);
+                if (survive) ps.q_next[at] = slot;
+                const uint32_t sat = warp_push(ps.counters + CTR_SHADOW, want_shadow);
+                if (want_shadow) ps.shadow[sat] = sr;
+            }
+        }
+
+        // ------------------------------------------------------------------ K8 shadow rays
+        template<bool COUNT>
+        __global__ void __launch_bounds__(256) k_shadow(DScene sc, PathState ps)
+        {
+            const uint32_t n = ps.counters[CTR_SHADOW];
+            TravCounters   tc;
+            for (;;)
+            {
+                const uint32_t base = warp_fetch(ps.counters + CTR_CUR_SHADOW);
+                if (base >= n) break;
+                const uint32_t idx = base + crb_lane_id();
+                if (idx < n)
+                {
+                    const ShadowRay sr = ps.shadow[idx];
+                    V3              o  = v3(sr.o.x, sr.o.y, sr.o.z);
+                    const V3        d  = v3(sr.d.x, sr.d.y, sr.d.z);
+                    const V3        dn = normalize(d);    // model.cpp:110-112
+                    bool            visible;
+                    if (!sc.has_alpha)
+                        visible = traverse<true, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), &tc).prim == INVALID_PRIM;
+                    else
+                    {
+                        // renderer.cpp:330-345: closest hit, marching through alpha cut-outs in 0.1 steps
+                        visible = false;
+                        for (int guard = 0; guard < 4096; guard++)
+                        {
+                            const Hit h = traverse<false, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), &tc);
+                            if (h.prim == INVALID_PRIM)
+                            {
+                                visible = true;
+                                break;
+                            }
+                            const Surface   sf  = surface_at(sc, o, dn, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
+                            const DMaterial mat = sc.materials[sf.mat];
+                            if (surface_colour(sc, mat, sf).w != 0.0f) break;
+                            o = sf.point + d * 0.1f;
+                        }
+                    }
+                    if (visible)
+                    {
+                        const uint32_t slot = __float_as_uint(sr.o.w);
+                        const float4   r4   = ps.rad[slot];
+                        const V3       r    = v3(r4.x, r4.y, r4.z) + v3(sr.c.x, sr.c.y, sr.c.z);
+                        ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
+                    }
+                }
+            }
+            if (COUNT)
+            {
+                atomicAdd(ps.stats + ST_NODES, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS, tc.tris);
+            }
+        }
+
+        // one thread: roll the queue counters over to the next bounce and keep the ray statistics
+        __global__ void k_advance(PathState ps, int last)
+        {
+            if (blockIdx.x * blockDim.x + threadIdx.x != 0) return;
+            uint32_t *c = ps.counters;
+            ps.stats[ST_CLOSEST] += c[CTR_IN];
+            ps.stats[ST_SHADOW] += c[CTR_SHADOW];
+            if (last) ps.stats[ST_RANOUT] += c[CTR_NEXT];
+            c[CTR_IN] = c[CTR_NEXT];
+            c[CTR_NEXT] = 0, c[CTR_SHADOW] = 0;
+            c[CTR_CLASS0] = c[CTR_CLASS0 + 1] = c[CTR_CLASS0 + 2] = c[CTR_CLASS0 + 3] = 0;
+            c[CTR_CUR_TRACE] = c[CTR_CUR_SHADE] = c[CTR_CUR_SHADOW] = 0;
+        }
+
+        __device__ __forceinline__ float4 resolve_px(float4 a, float n)
+        {
+            // renderer.cpp:371-383
+            const float g = 1.f / 2.2f;
+            return make_float4(powf(clampf(a.x / n, 0.0f, 1.0f), g), powf(clampf(a.y / n, 0.0f, 1.0f), g), powf(clampf(a.z / n, 0.0f, 1.0f), g), 1.0f);
+        }
+
+        // ------------------------------------------------------------------ K9 accumulate + resolve
+        __global__ void __launch_bounds__(256) k_accumulate(RenderParams rp, PathState ps, uint32_t passes_after)
+        {
+            const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+            if (pix >= rp.npix) return;
+            const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+            const uint32_t fi = flipped_index(rp, x, y);
+            float4         a  = rp.accum[fi];
+            for (uint32_t s = 0; s < rp.batch; s++)
+            {
+                const float4 r = ps.rad[size_t(s) * rp.npix + pix];    // coalesced float4, sample order = the reference's pass order
+                a.x += r.x, a.y += r.y, a.z += r.z;
+            }
+            a.w           = float(passes_after);
+            rp.accum[fi]  = a;
+            rp.display[fi] = resolve_px(a, float(passes_after));
+        }
+
+        __global__ void __launch_bounds__(256) k_resolve(const float4 *__restrict__ accum, float4 *__restrict__ display, uint32_t n, uint32_t passes)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            float4 a   = accum[i];
+            display[i] = resolve_px(a, float(passes));
+        }
+
+        __global__ void k_fill4(float4 *p, uint32_t n, float4 v)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i < n) p[i] = v;
+        }
+    }    // namespace
+
+    // ====================================================================== host side
+    Render::Render(Scene *s, uint32_t w_, uint32_t h_, uint32_t mb, uint32_t seed_, uint32_t flags_)
+        : scene(s), w(w_), h(h_), max_bounces(mb), seed(seed_), flags(flags_), row0(0), row1(h_)
+    {
+#ifndef CRB_EMU
+        CRB_CUDA_CHECK(cudaSetDevice(s->device));
+        cudaDeviceProp p;
+        CRB_CUDA_CHECK(cudaGetDeviceProperties(&p, s->device));
+        n_sms = p.multiProcessorCount;
+        CRB_CUDA_CHECK(cudaEventCreate(&ev0));
+        CRB_CUDA_CHECK(cudaEventCreate(&ev1));
+#endif
+        counters.alloc(CTR_COUNT);
+        dstats.alloc(ST_COUNT);
+        alloc_images();
+        reset();
+    }
+
+    Render::~Render()
+    {
+#ifndef CRB_EMU
+        cudaStreamSynchronize(stream());
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+#endif
+    }
+
+    void Render::alloc_images()
+    {
+        const size_t n = size_t(w) * h;
+        accum.alloc(n), display.alloc(n), albedo.alloc(n), normal.alloc(n), depth.alloc(n);
+    }
+
+    void Render::reset()
+    {
+        // renderer::start (renderer.cpp:154-170) zeroes _raw_buffer and clears _buffer; cr::image is
+        // FLT_MAX-filled on construction/clear (image.h:30-38)
+        collect_time();
+        const uint32_t n = w * h;
+        const float    mx = 3.402823466e+38f;
+        const float4   fm = make_float4(mx, mx, mx, mx);
+        dev_zero(accum.p, size_t(n) * 16, stream());
+        const unsigned g = (n + 255) / 256;
+        CRB_LAUNCH(k_fill4, g, 256, stream(), display.p, n, fm);
+        CRB_LAUNCH(k_fill4, g, 256, stream(), albedo.p, n, fm);
+        CRB_LAUNCH(k_fill4, g, 256, stream(), normal.p, n, fm);
+        CRB_LAUNCH(k_fill4, g, 256, stream(), depth.p, n, fm);
+        dev_zero(dstats.p, ST_COUNT * 8, stream());
+        dev_zero(counters.p, CTR_COUNT * 4, stream());
+        passes = 0, device_ms = 0, launches = 0, pixel_samples = 0;
+    }
+
+    void Render::set_resolution(uint32_t w_, uint32_t h_)
+    {
+        sync();
+        w = w_, h = h_, row0 = 0, row1 = h_;
+        alloc_images();
+        scene_version = ~0ull;
+        reset();
+    }
+
+    void Render::set_rows(uint32_t y0, uint32_t y1)
+    {
+        if (y1 > h) y1 = h;
+        if (y0 >= y1) throw Error(ERR_INVALID_ARG, "set_rows: empty row range");
+        row0 = y0, row1 = y1;
+    }
+
+    void Render::refresh()
+    {
+        scene->require_committed();
+        dscene        = scene->device_scene(w, h);
+        scene_version = scene->version;
+    }
+
+    void Render::ensure_paths(size_t n)
+    {
+        if (n <= capacity) return;
+        sync();
+        ray_o.alloc(n), ray_d.alloc(n), thr.alloc(n), rad.alloc(n), hit.alloc(n);
+        q_in.alloc(n), q_next.alloc(n);
+        for (auto &q : q_class) q.alloc(n);
+        shadow.alloc(n);
+        capacity = n;
+    }
+
+    void Render::collect_time()
+    {
+#ifndef CRB_EMU
+        if (ev_pending)
+        {
+            CRB_CUDA_CHECK(cudaEventSynchronize(ev1));
+            float ms = 0;
+            CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+            device_ms += ms;
+            ev_pending = false;
+        }
+#endif
+    }
+
+    void Render::render_samples(uint32_t first, uint32_t n)
+    {
+        if (n == 0) return;
+        if (scene_version != scene->version) refresh();
+        collect_time();
+        const uint32_t nrows = row1 - row0;
+        const uint32_t npix  = w * nrows;
+        uint32_t       spp_batch = uint32_t(std::max<size_t>(1, target_paths / npix));
+        spp_batch                = std::min(spp_batch, n);
+        ensure_paths(size_t(npix) * spp_batch);
+
+        PathState ps {};
+        ps.ray_o = ray_o.p, ps.ray_d = ray_d.p, ps.thr = thr.p, ps.rad = rad.p, ps.hit = hit.p;
+        ps.q_in = q_in.p, ps.q_next = q_next.p;
+        for (int c = 0; c < 4; c++) ps.q_class[c] = q_class[c].p;
+        ps.shadow = shadow.p, ps.counters = counters.p, ps.stats = dstats.p;
+
+        RenderParams rp {};
+        rp.w = w, rp.h = h, rp.row0 = row0, rp.nrows = nrows, rp.npix = npix, rp.seed = seed;
+        rp.aov_sample = first + n - 1;
+        rp.accum = accum.p, rp.display = display.p, rp.albedo = albedo.p, rp.normal = normal.p, rp.depth = depth.p;
+
+        const bool count = (flags & CRB_RENDER_FLAG_COUNTERS) != 0;
+#ifdef CRB_EMU
+        const unsigned pgrid = 1, pblock = 1;
+#else
+        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256;
+        CRB_CUDA_CHECK(cudaEventRecord(ev0, stream()));
+#endif
+        cudaStream_t st = stream();
+        for (uint32_t done = 0; done < n; done += spp_batch)
+        {
+            const uint32_t b  = std::min(spp_batch, n - done);
+            const uint32_t np = npix * b;
+            rp.first_sample = first + done, rp.batch = b;
+            // queue counters for bounce 0: everything is active
+            uint32_t init[CTR_COUNT] = {};
+            init[CTR_IN]             = np;
+            dev_upload(counters.p, init, sizeof(init), st);
+#ifdef CRB_EMU
+            CRB_LAUNCH(k_raygen, np, 1, st, dscene, rp, ps);
+#else
+            CRB_LAUNCH(k_raygen, (np + 255) / 256, 256, st, dscene, rp, ps);
+#endif
+            launches++;
+            for (uint32_t i = 0; i < max_bounces; i++)
+            {
+                rp.bounce = i;
+                if (count)
+                    CRB_LAUNCH((k_trace<true>), pgrid, pblock, st, dscene, ps);
+                else
+                    CRB_LAUNCH((k_trace<false>), pgrid, pblock, st, dscene, ps);
+                CRB_LAUNCH(k_shade, pgrid, pblock, st, dscene, rp, ps);
+                launches += 2;
+                if (dscene.sun.enabled)
+                {
+                    if (count)
+                        CRB_LAUNCH((k_shadow<true>), pgrid, pblock, st, dscene, ps);
+                    else
+                        CRB_LAUNCH((k_shadow<false>), pgrid, pblock, st, dscene, ps);
+                    launches++;
+                }
+                CRB_LAUNCH(k_advance, 1, 1, st, ps, int(i + 1 == max_bounces));
+                launches++;
+                std::swap(ps.q_in, ps.q_next);
+            }
+            passes += b;
+#ifdef CRB_EMU
+            CRB_LAUNCH(k_accumulate, npix, 1, st, rp, ps, passes);
+#else
+            CRB_LAUNCH(k_accumulate, (npix + 255) / 256, 256, st, rp, ps, passes);
+#endif
+            launches++;
+            pixel_samples += uint64_t(np);
+        }
+#ifndef CRB_EMU
+        CRB_CUDA_CHECK(cudaEventRecord(ev1, stream()));
+        ev_pending = true;
+#endif
+    }
+
+    void Render::sync()
+    {
+        stream_sync(stream());
+        collect_time();
+    }
+
+    void Render::resolve()
+    {
+        const uint32_t n = w * h;
+#ifdef CRB_EMU
+        CRB_LAUNCH(k_resolve, n, 1, stream(), accum.p, display.p, n, passes ? passes : 1u);
+#else
+        CRB_LAUNCH(k_resolve, (n + 255) / 256, 256, stream(), accum.p, display.p, n, passes ? passes : 1u);
+#endif
+    }
+
+    void Render::read(int kind, float *dst)
+    {
+        sync();
+        const float4 *src = nullptr;
+        switch (kind)
+        {
+        case CRB_RAW_SUM: src = accum.p; break;
+        case CRB_PROGRESS: src = display.p; break;
+        case CRB_ALBEDO: src = albedo.p; break;
+        case CRB_NORMAL: src = normal.p; break;
+        case CRB_DEPTH: src = depth.p; break;
+        default: throw Error(ERR_INVALID_ARG, "read: unknown buffer kind");
+        }
+        dev_download(dst, src, size_t(w) * h * 16, stream());
+    }
+
+    void Render::stats(crb_stats &out)
+    {
+        sync();
+        unsigned long long st[ST_COUNT];
+        dev_download(st, dstats.p, sizeof(st), stream());
+        out.total_queries   = st[ST_CLOSEST] + st[ST_SHADOW];
+        out.ref_rays        = st[ST_CLOSEST] + st[ST_RANOUT];    // renderer.cpp:271-272,356
+        out.pixel_samples   = pixel_samples;
+        out.passes          = passes;
+        out.device_ms       = device_ms;
+        out.kernel_launches = launches;
+        out.node_visits     = st[ST_NODES];
+        out.tri_tests       = st[ST_TRIS];
+    }
+}    // namespace crb

@@ -1,0 +1,88 @@
+// render.cuh — the wavefront path tracer that replaces cr::renderer's management thread, per-scanline
+// thread-pool tasks and _sample_pixel (src/render/renderer.cpp:116-144,240-384).
+#pragma once
+#include "scene.cuh"
+
+namespace crb
+{
+    struct ShadowRay    // 48 bytes
+    {
+        float4 o;    // xyz origin, w = path slot (bits)
+        float4 d;    // xyz direction as sampled (un-normalised), w unused
+        float4 c;    // rgb contribution added to the path if the sun is visible
+    };
+
+    // device pointers of the path-state SoA, indexed by path slot = sample_in_batch * npix + pixel
+    struct PathState
+    {
+        float4 *ray_o;    // xyz origin
+        float4 *ray_d;    // xyz direction exactly as the reference's cr::ray::direction (not re-normalised)
+        float4 *thr;      // xyz throughput
+        float4 *rad;      // xyz radiance ("final")
+        float4 *hit;      // t (normalised-direction units), u, v, flat prim (bits)
+        uint32_t *q_in;         // active path slots of this bounce
+        uint32_t *q_next;       // active path slots of the next bounce
+        uint32_t *q_class[4];   // after trace: 0 miss, 1 metal, 2 smooth, 3 glass (material sort)
+        ShadowRay *shadow;
+        uint32_t  *counters;    // see CTR_* below
+        unsigned long long *stats;    // see ST_* below
+    };
+    enum { CTR_IN = 0, CTR_CLASS0 = 1, CTR_NEXT = 5, CTR_SHADOW = 6, CTR_CUR_TRACE = 7, CTR_CUR_SHADE = 8, CTR_CUR_SHADOW = 9, CTR_COUNT = 16 };
+    enum { ST_CLOSEST = 0, ST_SHADOW = 1, ST_RANOUT = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
+
+    struct RenderParams
+    {
+        uint32_t w, h, row0, nrows, npix;    // npix = w * nrows (pixels rendered per pass)
+        uint32_t seed;
+        uint32_t first_sample, batch;        // this batch renders global samples first_sample .. +batch-1
+        uint32_t aov_sample;                 // global sample index whose first hit is written to the AOVs
+        uint32_t bounce;
+        float4  *accum, *display, *albedo, *normal, *depth;
+    };
+
+    struct Render
+    {
+        Scene   *scene;
+        uint32_t w, h, max_bounces, seed, flags;
+        uint32_t row0, row1;
+        uint32_t passes = 0;
+        uint64_t scene_version = ~0ull;
+        DScene   dscene;
+
+        DBuf<float4> accum, display, albedo, normal, depth;
+        // path state
+        size_t              capacity = 0;
+        DBuf<float4>        ray_o, ray_d, thr, rad, hit;
+        DBuf<uint32_t>      q_in, q_next, q_class[4];
+        DBuf<ShadowRay>     shadow;
+        DBuf<uint32_t>      counters;
+        DBuf<unsigned long long> dstats;
+        int      n_sms = 1;
+        double   device_ms = 0;
+        uint64_t launches  = 0;
+        uint64_t pixel_samples = 0;
+        size_t   target_paths = size_t(1) << 23;    // paths in flight per batch
+#ifndef CRB_EMU
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        bool        ev_pending = false;
+#endif
+
+        Render(Scene *s, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags);
+        ~Render();
+        cudaStream_t stream() const { return scene->stream; }
+        void reset();
+        void set_resolution(uint32_t w, uint32_t h);
+        void set_rows(uint32_t y0, uint32_t y1);
+        void refresh();
+        void render_samples(uint32_t first, uint32_t n);
+        void sync();
+        void resolve();
+        void read(int kind, float *dst);
+        void stats(crb_stats &out);
+
+    private:
+        void alloc_images();
+        void ensure_paths(size_t n);
+        void collect_time();
+    };
+}    // namespace crb

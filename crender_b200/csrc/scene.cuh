@@ -1,0 +1,148 @@
+// scene.cuh — host-side scene container and the device-resident scene the kernels read.
+//
+// Mirrors cr::scene + cr::registry (src/render/scene.h:19-52, src/render/entities/registry.cpp:51-97,
+// 248-256) and the component structs of src/render/entities/components.h:18-97. Where the reference
+// keeps one Embree scene per model and loops over models and instance transforms per ray
+// (scene.cpp:83-95, model.cpp:107-123), this design flattens every (model, instance) pair into one
+// world-space triangle array at commit time — HBM is 180 GB, a 10M-triangle flattened scene is <1 GB —
+// and builds ONE 8-wide BVH over it, so a ray does a single traversal with no per-ray matrix inverse.
+#pragma once
+#include "../../include/crender_b200.h"
+#include "bvh8.cuh"
+#include "bvh_build.cuh"
+#include "platform.cuh"
+
+#include <vector>
+
+namespace crb
+{
+    struct DMaterial    // 48 bytes, 16-byte aligned rows
+    {
+        float    colour[4];
+        uint32_t shade_type;
+        float    ior, reflectiveness, emission;
+        int32_t  tex;
+        uint32_t pad[3];
+    };
+
+    struct DTexture
+    {
+        uint32_t w, h;
+        uint32_t offset;    // into the float4 texel pool
+        uint32_t pad;
+    };
+
+    struct DCamera
+    {
+        float    position[3];
+        float    m[3][3];     // rotation part of _cached_matrix, m[column][row]
+        float    trans[3];    // translation column (orthographic origin)
+        float    w;           // 1/tan(fov/2)
+        float    scale;
+        uint32_t mode;
+        float    aspect;
+    };
+
+    struct DSun
+    {
+        float    dir[3];          // sun.direction
+        float    transform[9];    // mat3(tangent, normal, bitangent) of -dir, column-major
+        float    size, intensity;
+        float    colour[3];
+        float    one_minus_cos;   // 1 - cos(size)
+        float    pdf;             // 1/(tau*(1-cos(size)))
+        uint32_t enabled;
+    };
+
+    struct FlatRange    // flat primitive ids [start, start+ntris) belong to (model, inst)
+    {
+        uint32_t start, ntris, model, inst, src_start, pad[3];
+    };
+
+    // Everything a kernel needs, passed by value.
+    struct DScene
+    {
+        Bvh8            bvh;
+        const float4   *shade_tri;    // per SOURCE triangle: object-space unit normal (model.cpp:35), w = global material index
+        const float    *obj_uvs;      // 6 floats per source triangle, or nullptr
+        const uint32_t *flat_src;     // flat prim -> source triangle, or nullptr when identity
+        const DMaterial *materials;
+        const DTexture *textures;
+        const float4   *texels;
+        const float4   *skybox;
+        uint32_t        sky_w, sky_h;
+        float           sky_rot[2];
+        const FlatRange *ranges;
+        uint32_t        n_ranges;
+        uint32_t        has_alpha;    // any material that can produce colour.w == 0
+        DSun            sun;
+        DCamera         cam;
+    };
+
+    struct HostModel
+    {
+        uint32_t                  ntris = 0;
+        std::vector<float>        verts, uvs;
+        std::vector<uint32_t>     mat_idx;
+        std::vector<crb_material> materials;
+        std::vector<float>        transforms;    // 16 floats each, column-major
+    };
+    struct HostTexture
+    {
+        uint32_t           w, h;
+        std::vector<float> rgba;
+    };
+
+    struct Scene
+    {
+        int          device = 0;
+        cudaStream_t stream = nullptr;
+
+        std::vector<HostModel>   models;
+        std::vector<HostTexture> textures;
+        crb_sun                  sun;
+        bool                     sun_enabled = true;    // scene.h:45
+        std::vector<float>       skybox;
+        uint32_t                 sky_w = 0, sky_h = 0;
+        float                    sky_rot[2] = { 0, 0 };
+        crb_camera               camera;
+
+        // device state (valid after commit)
+        bool             committed = false;
+        uint64_t         version   = 0;    // bumped by every mutation/commit; renderers refresh on change
+        DBuf<float>      d_wverts;         // kept only during the build
+        DBuf<float4>     d_shade_tri;
+        DBuf<float>      d_obj_uvs;
+        DBuf<uint32_t>   d_flat_src;
+        DBuf<DMaterial>  d_materials;
+        DBuf<DTexture>   d_textures;
+        DBuf<float4>     d_texels;
+        DBuf<float4>     d_skybox;
+        DBuf<FlatRange>  d_ranges;
+        DBuf<uint4>      d_nodes;
+        DBuf<float4>     d_tris;
+        std::vector<FlatRange> ranges;
+        BuildStats       build;
+        double           upload_ms = 0;
+        uint32_t         n_flat    = 0;
+        bool             has_alpha = false;
+        double           last_query_ms = 0;
+
+        Scene();
+        ~Scene();
+        int  add_mesh(const float *verts, const float *uvs, const uint32_t *mat_idx, uint32_t ntris);
+        void set_materials(int model, const crb_material *m, uint32_t n);
+        void set_instances(int model, const float *mats, uint32_t n);
+        int  add_texture(const float *rgba, uint32_t w, uint32_t h);
+        void commit();
+        void upload_materials();    // also recomputes has_alpha
+        void upload_skybox();
+        DScene device_scene(uint32_t w, uint32_t h) const;    // camera aspect from the render target
+        void   require_committed() const;
+    };
+
+    // batch queries (trace.cu)
+    void intersect_batch(Scene &s, const crb_ray *rays, crb_hit *hits, uint64_t n, bool on_device);
+    void occluded_batch(Scene &s, const crb_ray *rays, uint8_t *occ, uint64_t n, bool on_device);
+    void trace_counters(Scene &s, const crb_ray *rays, uint64_t n, bool on_device, bool any_hit, uint64_t *nodes, uint64_t *tris);
+}    // namespace crb

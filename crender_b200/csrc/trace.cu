@@ -1,0 +1,169 @@
+// trace.cu — K5: batch closest-hit / any-hit queries (BASELINE config 3).
+//
+// Replaces cr::scene::cast_ray -> cr::model::intersect -> rtcIntersect1 called once per ray
+// (src/render/scene.cpp:79-98, src/objects/model.cpp:5-49,99-126) with one kernel over a ray array.
+// One thread per ray; rays are two coalesced 16-byte loads, the hit record is written as 24 bytes.
+#include "scene.cuh"
+
+#include <algorithm>
+
+namespace crb
+{
+    namespace
+    {
+        __device__ __forceinline__ void resolve_flat(const DScene &sc, uint32_t flat, uint32_t &prim, uint32_t &model, uint32_t &inst)
+        {
+            // ranges are sorted by start; binary search the range containing `flat`
+            uint32_t lo = 0, hi = sc.n_ranges;
+            while (hi - lo > 1)
+            {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (sc.ranges[mid].start <= flat) lo = mid; else hi = mid;
+            }
+            const FlatRange r = sc.ranges[lo];
+            prim = flat - r.start, model = r.model, inst = r.inst;
+        }
+
+        template<bool COUNT>
+        __global__ void __launch_bounds__(256) k_intersect_batch(DScene sc, const float4 *__restrict__ rays, uint64_t n, crb_hit *__restrict__ hits,
+                                                                 unsigned long long *ctr)
+        {
+            const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+            TravCounters   tc;
+            if (i < n)
+            {
+                const float4 a = rays[2 * i], b = rays[2 * i + 1];
+                const Hit    h = traverse<false, COUNT>(sc.bvh, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, b.w, &tc);
+                if (!COUNT)
+                {
+                    crb_hit out;
+                    out.t = h.t, out.u = h.u, out.v = h.v;
+                    out.prim = INVALID_PRIM, out.model = INVALID_PRIM, out.inst = 0;
+                    if (h.prim != INVALID_PRIM) resolve_flat(sc, h.prim, out.prim, out.model, out.inst);
+                    hits[i] = out;
+                }
+            }
+            if (COUNT)
+            {
+                atomicAdd(ctr + 0, tc.nodes);
+                atomicAdd(ctr + 1, tc.tris);
+            }
+        }
+
+        template<bool COUNT>
+        __global__ void __launch_bounds__(256) k_occluded_batch(DScene sc, const float4 *__restrict__ rays, uint64_t n, uint8_t *__restrict__ occ,
+                                                                unsigned long long *ctr)
+        {
+            const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+            TravCounters   tc;
+            if (i < n)
+            {
+                const float4 a = rays[2 * i], b = rays[2 * i + 1];
+                const Hit    h = traverse<true, COUNT>(sc.bvh, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, b.w, &tc);
+                if (!COUNT) occ[i] = h.prim != INVALID_PRIM ? 1 : 0;
+            }
+            if (COUNT)
+            {
+                atomicAdd(ctr + 0, tc.nodes);
+                atomicAdd(ctr + 1, tc.tris);
+            }
+        }
+
+        struct Timer
+        {
+#ifndef CRB_EMU
+            cudaEvent_t  e0 = nullptr, e1 = nullptr;
+            cudaStream_t s;
+            explicit Timer(cudaStream_t st) : s(st)
+            {
+                CRB_CUDA_CHECK(cudaEventCreate(&e0));
+                CRB_CUDA_CHECK(cudaEventCreate(&e1));
+            }
+            ~Timer()
+            {
+                if (e0) cudaEventDestroy(e0);
+                if (e1) cudaEventDestroy(e1);
+            }
+            void   start() { CRB_CUDA_CHECK(cudaEventRecord(e0, s)); }
+            double stop()
+            {
+                CRB_CUDA_CHECK(cudaEventRecord(e1, s));
+                CRB_CUDA_CHECK(cudaEventSynchronize(e1));
+                float ms = 0;
+                CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+                return ms;
+            }
+#else
+            explicit Timer(cudaStream_t) {}
+            void   start() {}
+            double stop() { return 0; }
+#endif
+        };
+
+        constexpr uint64_t CHUNK = 1ull << 24;    // rays per staging chunk for host-pointer calls
+
+        // mode 0 closest, 1 any-hit, 2 counters(closest), 3 counters(any)
+        void run_batch(Scene &s, const crb_ray *rays, void *out, uint64_t n, bool on_device, int mode, uint64_t *ctr_out)
+        {
+            s.require_committed();
+            if (n && (!rays || (mode < 2 && !out))) throw Error(ERR_INVALID_ARG, "batch query: null ray/result pointer");
+            const DScene sc = s.device_scene(1, 1);
+            Timer        timer(s.stream);
+            double       ms = 0;
+            DBuf<unsigned long long> d_ctr;
+            d_ctr.alloc(2);
+            dev_zero(d_ctr.p, 16, s.stream);
+            const size_t out_elem = mode == 0 ? sizeof(crb_hit) : 1;
+            DBuf<float4> d_rays;
+            DBuf<char>   d_out;
+            const int    B = 256;
+            for (uint64_t off = 0; off < n; off += CHUNK)
+            {
+                const uint64_t cnt = std::min<uint64_t>(CHUNK, n - off);
+                const float4  *rp;
+                char          *op;
+                if (on_device)
+                {
+                    rp = reinterpret_cast<const float4 *>(rays + off);
+                    op = static_cast<char *>(out) + off * out_elem;
+                }
+                else
+                {
+                    d_rays.ensure(cnt * 2);
+                    if (mode < 2) d_out.ensure(cnt * out_elem);
+                    dev_upload(d_rays.p, rays + off, cnt * sizeof(crb_ray), s.stream);
+                    rp = d_rays.p, op = d_out.p;
+                }
+                const unsigned g = unsigned((cnt + B - 1) / B);
+                timer.start();
+                switch (mode)
+                {
+                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, B, s.stream, sc, rp, cnt, reinterpret_cast<crb_hit *>(op), d_ctr.p); break;
+                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, B, s.stream, sc, rp, cnt, reinterpret_cast<uint8_t *>(op), d_ctr.p); break;
+                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, B, s.stream, sc, rp, cnt, (crb_hit *) nullptr, d_ctr.p); break;
+                default: CRB_LAUNCH((k_occluded_batch<true>), g, B, s.stream, sc, rp, cnt, (uint8_t *) nullptr, d_ctr.p); break;
+                }
+                ms += timer.stop();
+                if (!on_device && mode < 2) dev_download(static_cast<char *>(out) + off * out_elem, d_out.p, cnt * out_elem, s.stream);
+            }
+            if (ctr_out)
+            {
+                unsigned long long c[2];
+                dev_download(c, d_ctr.p, 16, s.stream);
+                ctr_out[0] = c[0], ctr_out[1] = c[1];
+            }
+            stream_sync(s.stream);
+            s.last_query_ms = ms;
+        }
+    }    // namespace
+
+    void intersect_batch(Scene &s, const crb_ray *rays, crb_hit *hits, uint64_t n, bool on_device) { run_batch(s, rays, hits, n, on_device, 0, nullptr); }
+    void occluded_batch(Scene &s, const crb_ray *rays, uint8_t *occ, uint64_t n, bool on_device) { run_batch(s, rays, occ, n, on_device, 1, nullptr); }
+    void trace_counters(Scene &s, const crb_ray *rays, uint64_t n, bool on_device, bool any_hit, uint64_t *nodes, uint64_t *tris)
+    {
+        uint64_t c[2] = { 0, 0 };
+        run_batch(s, rays, nullptr, n, on_device, any_hit ? 3 : 2, c);
+        if (nodes) *nodes = c[0];
+        if (tris) *tris = c[1];
+    }
+}    // namespace crb

@@ -1,0 +1,199 @@
+/*
+ * crender_b200.h — C ABI of the B200-native path-tracing core for CRender.
+ *
+ * The reference has no plugin/FFI interface: its hot path sits behind the in-process C++ classes
+ * cr::scene and cr::renderer that the ImGui layer calls. This header re-exports exactly that class
+ * surface as plain C (opaque handles, plain pointers and sizes, no C++/torch types) so that a
+ * maintainer can put it behind cr::scene / cr::renderer (see INTEGRATION.md for the shim), and so that
+ * tests/bench drive it through ctypes. Each entry point cites the reference interface it replaces
+ * (paths relative to the CRender source tree).
+ *
+ * Conventions
+ *  - every function returns 0 on success or a crb_status code; crb_last_error() gives the message of
+ *    the last failure on the calling thread. Nothing here ever calls exit() (the reference's
+ *    cr::exit(), src/util/exception.h:9-13, terminates the process; codes 30/31 are kept from
+ *    data/errors.json for geometry-buffer failures).
+ *  - the library owns all device memory; host arrays passed in are copied before the call returns.
+ *  - one host control thread per handle; work is asynchronous on the handle's CUDA stream until
+ *    crb_render_sync / crb_render_read (same contract as renderer::update = pause -> mutate -> start,
+ *    src/render/renderer.cpp:185-192).
+ *  - there is NO CPU fallback: without a CUDA device every call fails with CRB_ERR_NO_DEVICE.
+ */
+#ifndef CRENDER_B200_H
+#define CRENDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum crb_status
+{
+    CRB_OK                = 0,
+    CRB_ERR_GENERIC       = 1,  /* data/errors.json "1" */
+    CRB_ERR_INVALID_ARG   = 2,
+    CRB_ERR_NO_DEVICE     = 10,
+    CRB_ERR_CUDA          = 11,
+    CRB_ERR_OOM           = 12,
+    CRB_ERR_BUILD_VERTS   = 30, /* data/errors.json "30": could not create vertex buffer */
+    CRB_ERR_BUILD_INDEX   = 31, /* data/errors.json "31": could not create index buffer */
+    CRB_ERR_BVH_DEPTH     = 32,
+    CRB_ERR_NOT_COMMITTED = 33
+} crb_status;
+
+/* cr::material::type, src/render/material/material.h:14-19 (same numeric order) */
+enum { CRB_METAL = 0, CRB_SMOOTH = 1, CRB_GLASS = 2 };
+
+/* cr::material::information, src/render/material/material.h:31-41 */
+typedef struct crb_material
+{
+    uint32_t shade_type;     /* default CRB_SMOOTH */
+    float    ior;            /* 1.5 */
+    float    roughness;      /* 0.5 (dead in the reference: renderer.cpp:84-86 is commented out) */
+    float    reflectiveness; /* 1 */
+    float    emission;       /* 0 */
+    float    colour[4];      /* 1,1,1,1; colour[3]==0 is an alpha cut-out (renderer.cpp:37-41) */
+    int32_t  tex;            /* -1 none, else id from crb_scene_add_texture */
+} crb_material;
+
+/* cr::entity::sun, src/render/entities/components.h:23-29 */
+typedef struct crb_sun
+{
+    float size;         /* cone half-angle, default pi/48 */
+    float intensity;    /* 100 */
+    float direction[3]; /* normalize(0.8,-1,0) */
+    float colour[3];    /* 1,.9,.7 */
+} crb_sun;
+
+/* cr::camera, src/render/camera.h:11-41 */
+typedef struct crb_camera
+{
+    float    position[3]; /* default 5,5,0 */
+    float    rotation[3]; /* degrees: x about UP, y about RIGHT, z about FORWARD (camera.cpp:54-68) */
+    float    fov;         /* degrees, default 75 */
+    float    scale;       /* orthographic half-extent */
+    uint32_t mode;        /* 0 perspective, 1 orthographic */
+} crb_camera;
+
+/* RTCRay subset, src/objects/model.cpp:14-25 */
+typedef struct crb_ray
+{
+    float o[3], tmin;
+    float d[3], tmax;
+} crb_ray;
+
+/* RTCHit subset + which model/instance (cr::ray::intersection_record, src/render/ray.h:15-23) */
+typedef struct crb_hit
+{
+    float    t; /* +inf on miss, in units of |d| */
+    float    u, v;
+    uint32_t prim;  /* triangle index inside the model, 0xffffffff on miss */
+    uint32_t model; /* model id, 0xffffffff on miss */
+    uint32_t inst;  /* instance index inside the model */
+} crb_hit;
+
+typedef struct crb_build_info
+{
+    double   build_ms;  /* device time of the BVH build (the rtcCommitScene replacement) */
+    double   upload_ms; /* host->device copies + flattening */
+    uint64_t n_triangles; /* flattened world-space triangles (instances expanded) */
+    uint64_t n_nodes;     /* 8-wide nodes */
+    uint64_t node_bytes;
+    uint64_t tri_bytes;
+    uint32_t max_depth;
+    float    sah_cost;
+} crb_build_info;
+
+/* cr::renderer::renderer_stats, src/render/renderer.h:48-54, extended */
+typedef struct crb_stats
+{
+    uint64_t total_queries; /* closest-hit segments + shadow queries actually traced */
+    uint64_t ref_rays;      /* the reference's _total_rays rule (renderer.cpp:271-272,356) */
+    uint64_t pixel_samples;
+    uint64_t passes;        /* _current_sample */
+    double   device_ms;     /* device time spent in render kernels since reset */
+    uint64_t kernel_launches;
+    uint64_t node_visits;   /* only with CRB_RENDER_FLAG_COUNTERS / crb_trace_counters */
+    uint64_t tri_tests;
+} crb_stats;
+
+typedef struct crb_scene  crb_scene;
+typedef struct crb_render crb_render;
+
+const char *crb_last_error(void);
+/* selects the CUDA device for handles created afterwards by this thread; -1 = current */
+int crb_set_device(int device);
+int crb_device_info(char *name, int name_cap, int *sm_count, uint64_t *l2_bytes, uint64_t *hbm_bytes);
+
+/* ---- scene: cr::scene (src/render/scene.h:19-52) + cr::registry (src/render/entities/registry.h) */
+int crb_scene_create(crb_scene **out);
+int crb_scene_destroy(crb_scene *);
+/* scene::add_model -> registry::register_model (scene.cpp:31-34, registry.cpp:51-97): the de-indexed
+ * triangle soup (9 floats/tri), per-corner uvs (6 floats/tri, may be NULL), per-triangle material
+ * index. The default instance is the identity (registry.cpp:73-74). */
+int crb_scene_add_mesh(crb_scene *, const float *verts, const float *uvs, const uint32_t *mat_idx, uint32_t ntris, int *model_id);
+/* wholesale material replacement (src/ui/ui.h:924-929) */
+int crb_scene_set_materials(crb_scene *, int model_id, const crb_material *mats, uint32_t n);
+/* wholesale instance replacement, column-major glm::mat4 (src/ui/ui.h:1185-1191) */
+int crb_scene_set_instances(crb_scene *, int model_id, const float *mat4_colmajor, uint32_t n);
+/* cr::image RGBA f32 row-major (src/objects/image.h) registered as an entity (registry.cpp:77-90) */
+int crb_scene_add_texture(crb_scene *, const float *rgba, uint32_t w, uint32_t h, int *tex_id);
+/* registry::set_sun + scene::set_sun_enabled (registry.cpp:248-256, scene.cpp:115-123) */
+int crb_scene_set_sun(crb_scene *, const crb_sun *sun_or_null, int enabled);
+/* scene::set_skybox + set_skybox_rotation (scene.cpp:36-65); rgba NULL removes it */
+int crb_scene_set_skybox(crb_scene *, const float *rgba, uint32_t w, uint32_t h, float rot_u, float rot_v);
+/* whole-struct camera assignment (src/ui/ui.h:674-675) */
+int crb_scene_set_camera(crb_scene *, const crb_camera *);
+/* model::instance_geometry -> rtcCommitGeometry/rtcAttachGeometry/rtcCommitScene
+ * (src/objects/model.cpp:52-97): flatten instances, build the 8-wide BVH on the device. */
+int crb_scene_commit(crb_scene *, crb_build_info *info_or_null);
+
+/* ---- queries: scene::cast_ray -> model::intersect -> rtcIntersect1 (scene.cpp:79-98,
+ * model.cpp:5-49,99-126). rays/hits are host pointers unless on_device != 0. */
+int crb_intersect_batch(crb_scene *, const crb_ray *rays, crb_hit *hits, uint64_t n, int on_device);
+/* any-hit (rtcOccluded1 equivalent; the reference only ever calls rtcIntersect1) */
+int crb_occluded_batch(crb_scene *, const crb_ray *rays, uint8_t *occluded, uint64_t n, int on_device);
+/* instrumented traversal: mean node visits / triangle tests per ray for the roofline */
+int crb_trace_counters(crb_scene *, const crb_ray *rays, uint64_t n, int on_device, int any_hit, uint64_t *node_visits,
+                       uint64_t *tri_tests);
+/* device time of the last crb_intersect_batch / crb_occluded_batch kernel, ms */
+int crb_last_query_ms(crb_scene *, double *ms);
+
+/* ---- renderer: cr::renderer (src/render/renderer.h:24-105) */
+enum { CRB_RENDER_FLAG_COUNTERS = 1 };
+/* renderer::renderer(res_x,res_y,bounces,pool,scene) (renderer.cpp:106-145) + set_resolution's aspect
+ * (renderer.cpp:194-208). seed keys the counter-based sampler (DESIGN.md "Sampler"). */
+int crb_render_create(crb_scene *, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags, crb_render **out);
+int crb_render_destroy(crb_render *);
+/* renderer::start()'s clearing (renderer.cpp:154-170) */
+int crb_render_reset(crb_render *);
+int crb_render_set_resolution(crb_render *, uint32_t w, uint32_t h); /* renderer.cpp:194-208 */
+int crb_render_set_max_bounces(crb_render *, uint32_t bounces);      /* renderer.cpp:210-213 */
+/* picks up scene-side changes made since create (camera, sun, materials, re-commit) */
+int crb_render_refresh(crb_render *);
+/* restrict rendering to pixel rows [y0,y1) in sample space (tile partition); default full frame */
+int crb_render_set_rows(crb_render *, uint32_t y0, uint32_t y1);
+/* n progressive passes, global sample indices first_sample..first_sample+n-1
+ * (management thread + _get_tasks + _sample_pixel, renderer.cpp:116-144,240-384); asynchronous */
+int crb_render_samples(crb_render *, uint32_t first_sample, uint32_t n);
+int crb_render_sync(crb_render *);
+enum { CRB_RAW_SUM = 0, CRB_PROGRESS = 1, CRB_ALBEDO = 2, CRB_NORMAL = 3, CRB_DEPTH = 4 };
+/* current_progress/normals/albedos/depths (renderer.cpp:220-238): w*h*4 floats, row-major, x/y
+ * flipped exactly as the reference stores them. CRB_RAW_SUM = _raw_buffer as RGBA with A = passes. */
+int crb_render_read(crb_render *, int kind, float *dst_host);
+int crb_render_stats(crb_render *, crb_stats *out); /* renderer::current_stats, renderer.cpp:396-404 */
+/* multi-GPU plumbing: the float4 accumulation buffer (device pointer, w*h*4 floats) so that the
+ * caller's collective (torch.distributed/NCCL) can reduce it in place, then set the merged pass count
+ * and re-resolve the display buffer. */
+int crb_render_accum_ptr(crb_render *, void **device_ptr, uint64_t *n_floats);
+int crb_render_set_pass_count(crb_render *, uint32_t passes);
+int crb_render_resolve(crb_render *);
+/* the CUDA stream the handle launches on (cudaStream_t as void*) for event timing by the caller */
+int crb_render_stream(crb_render *, void **stream);
+int crb_scene_stream(crb_scene *, void **stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
