@@ -62,8 +62,12 @@ class Stats(C.Structure):
         ("passes", C.c_uint64),
         ("device_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
-        ("node_visits", C.c_uint64),
-        ("tri_tests", C.c_uint64),
+        ("node_visits", C.c_uint64 * 2),
+        ("tri_tests", C.c_uint64 * 2),
+        ("closest_queries", C.c_uint64),
+        ("shadow_queries", C.c_uint64),
+        ("kernel_ms", C.c_double * 8),
+        ("kernel_count", C.c_uint64 * 8),
     ]
 
 

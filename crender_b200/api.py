@@ -24,6 +24,7 @@ from ._capi import CrbError  # noqa: F401  (re-export)
 METAL, SMOOTH, GLASS = 0, 1, 2  # cr::material::type
 PERSPECTIVE, ORTHOGRAPHIC = 0, 1  # cr::camera::mode
 RAW_SUM, PROGRESS, ALBEDO, NORMAL, DEPTH = 0, 1, 2, 3, 4
+K_RAYGEN, K_TRACE, K_SHADE, K_SHADOW, K_ADVANCE, K_ACCUMULATE = range(6)  # crb_stats.kernel_ms index
 
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("model", "<u4"), ("inst", "<u4")])
@@ -235,11 +236,11 @@ class renderer:
     GPU grid replaces it. Progressive passes are requested explicitly with render(n) (the reference's
     management thread issues them in a loop until the target spp, renderer.cpp:116-144)."""
 
-    def __init__(self, res_x: int, res_y: int, bounces: int, scn: scene, seed: int = 0, counters: bool = False):
+    def __init__(self, res_x: int, res_y: int, bounces: int, scn: scene, seed: int = 0, counters: bool = False, timers: bool = False):
         self._lib = scn._lib
         self._scene = scn
         h = C.c_void_p()
-        _capi.check(self._lib, self._lib.crb_render_create(scn._h, res_x, res_y, bounces, seed, 1 if counters else 0, C.byref(h)))
+        _capi.check(self._lib, self._lib.crb_render_create(scn._h, res_x, res_y, bounces, seed, (1 if counters else 0) | (2 if timers else 0), C.byref(h)))
         self._h = h
         self._res = (res_x, res_y)
         self._spp_target = 0

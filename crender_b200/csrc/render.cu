@@ -437,8 +437,8 @@ namespace crb
             }
             if (COUNT)
             {
-                atomicAdd(ps.stats + ST_NODES, tc.nodes);
-                atomicAdd(ps.stats + ST_TRIS, tc.tris);
+                atomicAdd(ps.stats + ST_NODES_SHADOW, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS_SHADOW, tc.tris);
             }
         }
 
@@ -520,6 +520,8 @@ namespace crb
         cudaStreamSynchronize(stream());
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (const Timed &t : timed) cudaEventDestroy(t.a), cudaEventDestroy(t.b);
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
 #endif
     }
 
@@ -546,6 +548,7 @@ namespace crb
         dev_zero(dstats.p, ST_COUNT * 8, stream());
         dev_zero(counters.p, CTR_COUNT * 4, stream());
         passes = 0, device_ms = 0, launches = 0, pixel_samples = 0;
+        for (int i = 0; i < 8; i++) kernel_ms[i] = 0, kernel_count[i] = 0;
     }
 
     void Render::set_resolution(uint32_t w_, uint32_t h_)
@@ -593,6 +596,49 @@ namespace crb
             device_ms += ms;
             ev_pending = false;
         }
+        for (const Timed &t : timed)
+        {
+            CRB_CUDA_CHECK(cudaEventSynchronize(t.b));
+            float ms = 0;
+            CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, t.a, t.b));
+            kernel_ms[t.cls] += ms;
+            kernel_count[t.cls]++;
+            ev_pool.push_back(t.a), ev_pool.push_back(t.b);
+        }
+        timed.clear();
+#endif
+    }
+
+#ifndef CRB_EMU
+    cudaEvent_t Render::take_event()
+    {
+        if (!ev_pool.empty())
+        {
+            cudaEvent_t e = ev_pool.back();
+            ev_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        CRB_CUDA_CHECK(cudaEventCreate(&e));
+        return e;
+    }
+#endif
+    void Render::tick(int cls)
+    {
+#ifndef CRB_EMU
+        if (!(flags & CRB_RENDER_FLAG_TIMERS)) return;
+        Timed t { cls, take_event(), take_event() };
+        CRB_CUDA_CHECK(cudaEventRecord(t.a, stream()));
+        timed.push_back(t);
+#else
+        (void) cls;
+#endif
+    }
+    void Render::tock()
+    {
+#ifndef CRB_EMU
+        if (!(flags & CRB_RENDER_FLAG_TIMERS)) return;
+        CRB_CUDA_CHECK(cudaEventRecord(timed.back().b, stream()));
 #endif
     }
 
@@ -638,27 +684,37 @@ namespace crb
 #ifdef CRB_EMU
             CRB_LAUNCH(k_raygen, np, 1, st, dscene, rp, ps);
 #else
+            tick(CRB_K_RAYGEN);
             CRB_LAUNCH(k_raygen, (np + 255) / 256, 256, st, dscene, rp, ps);
+            tock();
 #endif
             launches++;
             for (uint32_t i = 0; i < max_bounces; i++)
             {
                 rp.bounce = i;
+                tick(CRB_K_TRACE);
                 if (count)
                     CRB_LAUNCH((k_trace<true>), pgrid, pblock, st, dscene, ps);
                 else
                     CRB_LAUNCH((k_trace<false>), pgrid, pblock, st, dscene, ps);
+                tock();
+                tick(CRB_K_SHADE);
                 CRB_LAUNCH(k_shade, pgrid, pblock, st, dscene, rp, ps);
+                tock();
                 launches += 2;
                 if (dscene.sun.enabled)
                 {
+                    tick(CRB_K_SHADOW);
                     if (count)
                         CRB_LAUNCH((k_shadow<true>), pgrid, pblock, st, dscene, ps);
                     else
                         CRB_LAUNCH((k_shadow<false>), pgrid, pblock, st, dscene, ps);
+                    tock();
                     launches++;
                 }
+                tick(CRB_K_ADVANCE);
                 CRB_LAUNCH(k_advance, 1, 1, st, ps, int(i + 1 == max_bounces));
+                tock();
                 launches++;
                 std::swap(ps.q_in, ps.q_next);
             }
@@ -666,7 +722,9 @@ namespace crb
 #ifdef CRB_EMU
             CRB_LAUNCH(k_accumulate, npix, 1, st, rp, ps, passes);
 #else
+            tick(CRB_K_ACCUMULATE);
             CRB_LAUNCH(k_accumulate, (npix + 255) / 256, 256, st, rp, ps, passes);
+            tock();
 #endif
             launches++;
             pixel_samples += uint64_t(np);
@@ -720,7 +778,9 @@ namespace crb
         out.passes          = passes;
         out.device_ms       = device_ms;
         out.kernel_launches = launches;
-        out.node_visits     = st[ST_NODES];
-        out.tri_tests       = st[ST_TRIS];
+        out.node_visits[0] = st[ST_NODES], out.node_visits[1] = st[ST_NODES_SHADOW];
+        out.tri_tests[0] = st[ST_TRIS], out.tri_tests[1] = st[ST_TRIS_SHADOW];
+        out.closest_queries = st[ST_CLOSEST], out.shadow_queries = st[ST_SHADOW];
+        for (int i = 0; i < 8; i++) out.kernel_ms[i] = kernel_ms[i], out.kernel_count[i] = kernel_count[i];
     }
 }    // namespace crb

@@ -28,7 +28,7 @@ namespace crb
         unsigned long long *stats;    // see ST_* below
     };
     enum { CTR_IN = 0, CTR_CLASS0 = 1, CTR_NEXT = 5, CTR_SHADOW = 6, CTR_CUR_TRACE = 7, CTR_CUR_SHADE = 8, CTR_CUR_SHADOW = 9, CTR_COUNT = 16 };
-    enum { ST_CLOSEST = 0, ST_SHADOW = 1, ST_RANOUT = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
+    enum { ST_CLOSEST = 0, ST_SHADOW = 1, ST_RANOUT = 2, ST_NODES = 3, ST_TRIS = 4, ST_NODES_SHADOW = 5, ST_TRIS_SHADOW = 6, ST_COUNT = 8 };
 
     struct RenderParams
     {
@@ -62,10 +62,23 @@ namespace crb
         uint64_t launches  = 0;
         uint64_t pixel_samples = 0;
         size_t   target_paths = size_t(1) << 23;    // paths in flight per batch
+        double   kernel_ms[8]    = {};
+        uint64_t kernel_count[8] = {};
 #ifndef CRB_EMU
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         bool        ev_pending = false;
+        // CRB_RENDER_FLAG_TIMERS: event pairs around every launch, resolved at sync()
+        struct Timed
+        {
+            int         cls;
+            cudaEvent_t a, b;
+        };
+        std::vector<Timed>       timed;
+        std::vector<cudaEvent_t> ev_pool;
+        cudaEvent_t              take_event();
 #endif
+        void tick(int cls);    // call before a launch
+        void tock();           // call after it
 
         Render(Scene *s, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags);
         ~Render();

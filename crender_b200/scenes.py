@@ -315,7 +315,7 @@ def textured_scene(seed: int = 7) -> SceneDesc:
     fence = _quad((-1.5, 0, 0.2), (-1.5, 1.2, 0.2), (1.5, 1.2, 0.2), (1.5, 0, 0.2)).astype(np.float32)  # -z facing
     fuv = np.array([[[0, 0], [0, 1], [2, 1]], [[0, 0], [2, 1], [2, 0]]], np.float32)
     m_fence = MeshDesc(fence, np.zeros(2, np.uint32), [material(SMOOTH, tex=1, name="cutout")], uvs=fuv, name="fence")
-    box = _box((0, 0.35, 0), (0.3, 0.35, 0.3), 0.0).astype(np.float32)
+    box = _box((0, 0.37, 0), (0.3, 0.35, 0.3), 0.0).astype(np.float32)
     inst = np.stack([translation(-1.0, 0, 1.2), compose(translation(1.0, 0.0, 1.4), rotation_y(30.0)), translation(0.0, 0.0, 2.2)])
     bm = [material(SMOOTH, colour=(0.8, 0.4, 0.3, 1), name="clay"), material(METAL, colour=(0.9, 0.9, 0.9, 1), reflectiveness=0.8), material(GLASS, ior=1.4)]
     bidx = np.asarray([0] * 4 + [1] * 4 + [2] * 4, np.uint32)

@@ -114,9 +114,17 @@ typedef struct crb_stats
     uint64_t passes;        /* _current_sample */
     double   device_ms;     /* device time spent in render kernels since reset */
     uint64_t kernel_launches;
-    uint64_t node_visits;   /* only with CRB_RENDER_FLAG_COUNTERS / crb_trace_counters */
-    uint64_t tri_tests;
+    /* only with CRB_RENDER_FLAG_COUNTERS: traversal work, closest-hit ([0]) and shadow ([1]) kernels */
+    uint64_t node_visits[2];
+    uint64_t tri_tests[2];
+    uint64_t closest_queries; /* total_queries = closest_queries + shadow_queries */
+    uint64_t shadow_queries;
+    /* only with CRB_RENDER_FLAG_TIMERS: device ms and launch count per kernel class, CUDA events around
+     * every launch on the handle's stream. index: CRB_K_* */
+    double   kernel_ms[8];
+    uint64_t kernel_count[8];
 } crb_stats;
+enum { CRB_K_RAYGEN = 0, CRB_K_TRACE = 1, CRB_K_SHADE = 2, CRB_K_SHADOW = 3, CRB_K_ADVANCE = 4, CRB_K_ACCUMULATE = 5 };
 
 typedef struct crb_scene  crb_scene;
 typedef struct crb_render crb_render;
@@ -161,7 +169,7 @@ int crb_trace_counters(crb_scene *, const crb_ray *rays, uint64_t n, int on_devi
 int crb_last_query_ms(crb_scene *, double *ms);
 
 /* ---- renderer: cr::renderer (src/render/renderer.h:24-105) */
-enum { CRB_RENDER_FLAG_COUNTERS = 1 };
+enum { CRB_RENDER_FLAG_COUNTERS = 1, CRB_RENDER_FLAG_TIMERS = 2 };
 /* renderer::renderer(res_x,res_y,bounces,pool,scene) (renderer.cpp:106-145) + set_resolution's aspect
  * (renderer.cpp:194-208). seed keys the counter-based sampler (DESIGN.md "Sampler"). */
 int crb_render_create(crb_scene *, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags, crb_render **out);

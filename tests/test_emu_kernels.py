@@ -1,0 +1,35 @@
+"""Kernel-logic checks on CPU: the product's kernel bodies (BVH build, wide-node collapse, traversal,
+wavefront shading) compiled by g++ in CRB_EMU mode (tests/emu) and compared with the oracle. With the same
+libm on both sides the comparison is exact. This is a development/test tool only; the GPU parity tests
+(test_gpu_parity.py) are the real gate."""
+import pytest
+
+import common
+import parity_cases as pc
+from crender_b200 import scenes
+
+
+@pytest.mark.parametrize("name", ["cornell", "mesh", "textured", "terrain"])
+def test_hits_match_oracle(oracle, emu_lib, name):
+    pc.check_hits(oracle, emu_lib, common.small_scenes()[name], n_rays=8000)
+
+
+@pytest.mark.parametrize("name,w,h,spp,bounces", [("cornell", 40, 40, 3, 8), ("mesh", 48, 32, 2, 5), ("textured", 48, 36, 3, 6), ("terrain", 40, 24, 2, 4)])
+def test_images_match_oracle(oracle, emu_lib, name, w, h, spp, bounces):
+    desc = common.small_scenes()[name]
+    identity_only = all(m.instances is None for m in desc.meshes)
+    pc.check_image(oracle, emu_lib, desc, w, h, spp, bounces, exact=identity_only)
+    pc.check_primary_hits(oracle, emu_lib, desc, w, h, exact=identity_only)
+
+
+def test_partition_invariance(emu_lib):
+    pc.check_partition_invariance(emu_lib, scenes.mesh_scene(24, 12), 30, 20, 4, 4)
+
+
+def test_edge_cases(emu_lib):
+    pc.check_edge_cases(emu_lib)
+
+
+def test_larger_build(oracle, emu_lib):
+    # 80k triangles: exercises deeper trees, many collapse levels and duplicate Morton keys
+    pc.check_hits(oracle, emu_lib, scenes.mesh_scene(200, 200, with_ground=False), n_rays=4000)

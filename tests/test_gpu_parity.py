@@ -1,0 +1,144 @@
+"""GPU parity tests proper: the CUDA path through the C ABI (libcrender_b200.so) against the oracle.
+
+Bars (BASELINE.json north_star): batch/primary hit primitive ids agree on >= 99.99 % of rays with |dt|/t <=
+1e-5 (bit-exact where no instance transform is involved: the triangle test is the same IEEE sequence on
+both sides); images within 1 % relative RMSE at equal spp with the same sampler seeds. At full size
+(1M triangles, 1080p) the oracle is too slow for whole images, so full-size checks use (a) the oracle on a
+bounded ray sample and (b) size-independent properties (partition invariance, any-hit == closest-hit
+existence, barycentric reconstruction)."""
+import numpy as np
+import pytest
+
+import common
+import parity_cases as pc
+from crender_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["cornell", "mesh", "textured", "terrain"])
+def test_hits_match_oracle(oracle, product_lib, name):
+    pc.check_hits(oracle, product_lib, common.small_scenes()[name], n_rays=200000)
+
+
+@pytest.mark.parametrize("name,w,h,spp,bounces", [("cornell", 128, 128, 16, 8), ("mesh", 160, 90, 8, 8), ("textured", 160, 120, 8, 6), ("terrain", 160, 90, 4, 5)])
+def test_images_match_oracle(oracle, product_lib, name, w, h, spp, bounces):
+    desc = common.small_scenes()[name]
+    pc.check_image(oracle, product_lib, desc, w, h, spp, bounces)
+    pc.check_primary_hits(oracle, product_lib, desc, w, h)
+
+
+def test_cornell_config1_full(oracle, product_lib):
+    # BASELINE config 1 at full size: 512x512, 64 spp, depth 8
+    err = pc.check_image(oracle, product_lib, scenes.cornell(), 512, 512, 64, 8)
+    assert err < 0.01
+
+
+def test_partition_invariance_small(product_lib):
+    pc.check_partition_invariance(product_lib, scenes.mesh_scene(60, 30), 200, 120, 8, 6)
+
+
+def test_edge_cases(product_lib):
+    pc.check_edge_cases(product_lib)
+
+
+def test_orthographic_and_rotated_camera(oracle, product_lib):
+    desc = scenes.cornell()
+    desc.cam = api.camera(position=(0.2, 0.1, -3.0), fov=50.0, rotation=(6.0, -4.0, 10.0))
+    pc.check_image(oracle, product_lib, desc, 96, 64, 4, 5)
+    desc.cam = api.camera(position=(0.0, 0.0, -3.0), current_mode=api.ORTHOGRAPHIC, scale=1.1)
+    pc.check_image(oracle, product_lib, desc, 96, 64, 4, 5)
+
+
+@pytest.fixture(scope="module")
+def big(product_lib):
+    desc = scenes.mesh_scene(1000, 500)  # 1M triangles + ground (BASELINE config 2/3)
+    g = api.scene(lib_path=product_lib)
+    scenes.load(desc, g)
+    info = g.commit()
+    assert info.n_triangles == 1000002
+    return desc, g, info
+
+
+def test_1m_batch_vs_oracle(oracle, big):
+    # config 3 on a bounded sample: 2M rays against the oracle's BVH (itself pinned to brute force)
+    desc, g, info = big
+    o = oracle.scene()
+    scenes.load(desc, o)
+    o.commit()
+    lo, hi = desc.aabb()
+    rays = scenes.random_rays(lo, hi, 2_000_000, seed=2)
+    hg, ho = g.cast_rays(rays), o.cast_rays(rays)
+    for f in ("prim", "model", "inst", "t", "u", "v"):
+        np.testing.assert_array_equal(hg[f], ho[f], err_msg=f)
+    sub = rays[:2000]
+    hb = o.cast_rays(sub, brute=True)
+    np.testing.assert_array_equal(hb["prim"], hg["prim"][:2000])
+    occ = g.occluded(rays)
+    np.testing.assert_array_equal(occ.astype(bool), hg["prim"] != common.MISS)
+
+
+def test_1m_properties_full_size(big):
+    # size-independent properties at BASELINE's full ray count scale (16M rays here; bench runs 100M)
+    desc, g, info = big
+    lo, hi = desc.aabb()
+    rays = scenes.random_rays(lo, hi, 16_000_000, seed=4)
+    h = g.cast_rays(rays)
+    hit = h["prim"] != common.MISS
+    assert 0.05 < hit.mean() < 0.95
+    assert np.all(np.isinf(h["t"][~hit])) and np.all(h["t"][hit] > 1e-5)
+    assert np.all((h["u"][hit] >= 0) & (h["v"][hit] >= 0) & (h["u"][hit] + h["v"][hit] <= 1.0 + 1e-6))
+    # barycentric reconstruction: o + t d == v0 + u e1 + v e2 (on a subset, in float64)
+    idx = np.flatnonzero(hit)[:200000]
+    tris = np.concatenate([m.verts for m in desc.meshes])  # identity instances: flat id = model offset + prim
+    off = np.cumsum([0] + [m.verts.shape[0] for m in desc.meshes])
+    flat = off[h["model"][idx]] + h["prim"][idx]
+    v = tris[flat].astype(np.float64)
+    p_ray = rays["o"][idx].astype(np.float64) + h["t"][idx, None].astype(np.float64) * rays["d"][idx]
+    p_tri = v[:, 0] + h["u"][idx, None] * (v[:, 1] - v[:, 0]) + h["v"][idx, None] * (v[:, 2] - v[:, 0])
+    assert np.abs(p_ray - p_tri).max() < 2e-4
+    # shortening tmax to just before the hit turns every hit into a miss; to the hit itself keeps it
+    r2 = rays[idx].copy()
+    r2["tmax"] = h["t"][idx]
+    assert np.all(g.cast_rays(r2)["prim"] == h["prim"][idx])
+    r2["tmax"] = h["t"][idx] * np.float32(0.999)
+    h3 = g.cast_rays(r2)
+    assert np.all((h3["prim"] == common.MISS) | (h3["t"] < h["t"][idx]))
+
+
+def test_1m_render_partition_invariance_1080p(big):
+    # BASELINE config 2 geometry at 1920x1080: splitting samples or rows must not change one bit
+    desc, g, info = big
+    r = api.renderer(1920, 1080, 8, g, seed=0)
+    r.render(4)
+    whole = r.raw_sum().copy()
+    assert np.isfinite(whole).all() and whole[..., :3].mean() > 0
+    r.start()
+    r.render(1, first_sample=0)
+    r.render(3, first_sample=1)
+    np.testing.assert_array_equal(r.raw_sum(), whole)
+    r.start()
+    for y0, y1 in ((0, 400), (400, 1080)):
+        r.set_rows(y0, y1)
+        r.render(4, first_sample=0)
+    np.testing.assert_array_equal(r.raw_sum()[..., :3], whole[..., :3])
+
+
+def test_1m_render_rows_vs_oracle(oracle, big):
+    # the oracle renders a 24-row band of the 1080p frame of config 2; the GPU band must match it
+    desc, g, info = big
+    o = oracle.scene()
+    scenes.load(desc, o)
+    o.commit()
+    w, h, y0, y1, spp = 1920, 1080, 520, 544, 4
+    ro = oracle.renderer(w, h, 8, o, seed=0)
+    ro.set_rows(y0, y1)
+    ro.render(spp)
+    rg = api.renderer(w, h, 8, g, seed=0)
+    rg.set_rows(y0, y1)
+    rg.render(spp)
+    # sample-space rows y0..y1 land at flipped rows h-1-y (renderer.cpp:358-362)
+    a = rg.raw_sum()[h - y1 : h - y0, :, :3]
+    b = ro.raw_sum()[h - y1 : h - y0, :, :3]
+    assert b.mean() > 0
+    assert common.relrmse(a, b) <= pc.IMG_RELRMSE
