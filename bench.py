@@ -72,20 +72,28 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        import tempfile
+
+        self.path = os.path.join(tempfile.gettempdir(), f"crb_clocks_{os.getpid()}.csv")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-f", self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            time.sleep(0.25)  # let the first sample land before the timed region starts
         except Exception:
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+            try:
+                self.rows = [[c.strip() for c in line.split(",")] for line in open(self.path) if line.strip()]
+                os.unlink(self.path)
+            except Exception:
+                self.rows = []
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:

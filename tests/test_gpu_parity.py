@@ -125,12 +125,14 @@ def test_1m_render_partition_invariance_1080p(big):
 
 
 def test_1m_render_rows_vs_oracle(oracle, big):
-    # the oracle renders a 24-row band of the 1080p frame of config 2; the GPU band must match it
+    # the oracle renders a 24-row band of the 1080p frame of config 2; the GPU band must match it.
+    # 32 spp: mirror/glass bounces on the 1M-triangle surface amplify the 1-ulp sinf/cosf differences between
+    # libm and libdevice, so a few paths diverge; the 1 % bar is for converged images (north_star)
     desc, g, info = big
     o = oracle.scene()
     scenes.load(desc, o)
     o.commit()
-    w, h, y0, y1, spp = 1920, 1080, 520, 544, 4
+    w, h, y0, y1, spp = 1920, 1080, 520, 544, 32
     ro = oracle.renderer(w, h, 8, o, seed=0)
     ro.set_rows(y0, y1)
     ro.render(spp)
