@@ -182,4 +182,147 @@ namespace crb
         if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
         return best;
     }
+
+    // ------------------------------------------------------------------------------------------------
+    // Persistent trace loop with per-lane dynamic refill.
+    //
+    // Incoherent rays have wildly different traversal lengths (a ray that misses the scene box needs one
+    // node, a grazing ray 50+), so "one warp = 32 fixed rays" leaves most lanes idle while the longest ray
+    // finishes (measured: 6 of 32 lanes active per issued instruction, profiles/r1a_k_trace.md). Here a
+    // warp is a pool of 32 traversal lanes: whenever lanes are idle, the warp takes exactly that many new
+    // work items from the global cursor with ONE atomic (warp-aggregated), and every lane keeps its own
+    // traversal state in registers. Lanes reconverge every STEPS node iterations, where finished rays are
+    // handed to `sink` (which may itself use warp-aggregated queue pushes) and idle lanes are refilled.
+    //
+    //   source(idx, item, o, d, tmin, tmax)  loads work item idx (called by the lane that owns it)
+    //   sink(valid, item, hit)               called by ALL lanes at a convergent point; valid lanes retire
+    template<bool ANY, bool COUNT, int STEPS, typename Source, typename Sink>
+    __device__ __forceinline__ void trace_persistent(const Bvh8 &bvh, uint32_t *cursor, uint32_t n, uint32_t chunk_max, Source source, Sink sink,
+                                                     TravCounters *ctr)
+    {
+        const unsigned FULL = 0xffffffffu;
+        const unsigned lane = crb_lane_id();
+        uint2          stack[BVH8_STACK];
+        int            sp = 0;
+        bool           active = false, finished = false, exhausted = false;
+        uint32_t       item = 0;
+        V3             o = v3(0, 0, 0), d = v3(0, 0, 1), idir = v3(0, 0, 0);
+        unsigned       octinv = 0;
+        float          tmin = 0.f;
+        Hit            best { 0.f, 0.f, 0.f, INVALID_PRIM };
+        uint2          group = make_uint2(0u, 0u);
+        uint32_t       local_next = 0, local_end = 0;
+        // reservation granularity: large enough to keep the cursor atomic rare, small enough that the last
+        // ranges are spread over all warps of the grid
+        const uint32_t total_warps = (gridDim.x * blockDim.x + CRB_WARP - 1) / CRB_WARP;
+        uint32_t       chunk       = n / (total_warps * 4u);
+        chunk                      = chunk < uint32_t(CRB_WARP) ? uint32_t(CRB_WARP) : (chunk > chunk_max ? chunk_max : chunk);
+
+        for (;;)
+        {
+            sink(finished, item, best);
+            finished = false;
+
+            const unsigned idle = __ballot_sync(FULL, !active);
+            if (idle != 0u && !exhausted)
+            {
+                // the warp owns a reserved range [local_next, local_end) of work items; a new range is
+                // reserved with one atomic only when it runs dry (same-address atomics serialise in L2)
+                const uint32_t need = uint32_t(__popc(idle));
+                if (local_next == local_end)
+                {
+                    const uint32_t want = chunk_max ? chunk : need;    // chunk_max == 0: reserve exactly what is idle
+                    uint32_t       b    = 0;
+                    if (lane == 0) b = atomicAdd(cursor, want);
+                    b          = __shfl_sync(FULL, b, 0);
+                    local_next = b < n ? b : n;
+                    local_end  = b + want < n ? b + want : n;
+                    if (local_next == local_end) exhausted = true;    // warp-uniform
+                }
+                const uint32_t avail = local_end - local_next;
+                const uint32_t rank  = uint32_t(__popc(idle & ((1u << lane) - 1u)));
+                const uint32_t base  = local_next;
+                local_next += need < avail ? need : avail;
+                if (!active)
+                {
+                    const uint32_t idx = base + rank;
+                    if (rank < avail)
+                    {
+                        float tmax;
+                        source(idx, item, o, d, tmin, tmax);
+                        best = Hit { tmax, 0.0f, 0.0f, INVALID_PRIM };
+                        if (bvh.n_nodes == 0)
+                        {
+                            best.t   = __int_as_float(0x7f800000);
+                            finished = true;
+                        }
+                        else
+                        {
+                            idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+                            octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+                            group  = make_uint2(0u, 0x80000000u);
+                            sp     = 0;
+                            active = true;
+                        }
+                    }
+                }
+            }
+            if (__ballot_sync(FULL, active || finished) == 0u) break;
+
+#pragma unroll 1
+            for (int it = 0; it < STEPS; it++)
+            {
+                if (active)
+                {
+                    const int bit = 31 - __clz(int(group.y & 0xff000000u));
+                    group.y &= ~(1u << bit);
+                    if (group.y & 0xff000000u) stack[sp++] = group;
+                    const unsigned slot       = unsigned(bit - 24) ^ octinv;
+                    const unsigned node_index = group.x + __popc(group.y & 0xffu & ((1u << slot) - 1u));
+
+                    const uint4 *np = bvh.nodes + size_t(node_index) * 5;
+                    const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                    if (COUNT) ctr->nodes++;
+                    const unsigned h = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, best.t);
+                    group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
+                    uint2 tgroup     = make_uint2(n1.y, h & 0x00ffffffu);
+                    bool  done       = false;
+
+                    while (tgroup.y)
+                    {
+                        const int i = __ffs(int(tgroup.y)) - 1;
+                        tgroup.y &= tgroup.y - 1;
+                        const float4 *tp = bvh.tris + size_t(tgroup.x + unsigned(i)) * 3;
+                        const float4  a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        if (COUNT) ctr->tris++;
+                        float t, u, v;
+                        if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, best.t, t, u, v))
+                        {
+                            const unsigned prim = __float_as_uint(a.w);
+                            if (ANY)
+                            {
+                                best = Hit { t, u, v, prim };
+                                done = true;
+                                break;
+                            }
+                            if (t < best.t || prim < best.prim) best = Hit { t, u, v, prim };
+                        }
+                    }
+
+                    if (!done && (group.y & 0xff000000u) == 0)
+                    {
+                        if (sp == 0)
+                            done = true;
+                        else
+                            group = stack[--sp];
+                    }
+                    if (done)
+                    {
+                        if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
+                        active = false, finished = true;
+                    }
+                }
+            }
+        }
+    }
 }    // namespace crb

@@ -36,9 +36,11 @@ namespace crb
             int    *left, *right;          // children refs
             int    *parent;                // parent of inner node (-1 for root)
             int    *leaf_parent;           // parent of leaf (sorted position)
-            int    *first, *last;          // sorted-position range covered by inner node
+            int    *count;                 // triangles below the inner node (set by refit, kept by treelets)
             float4 *lo, *hi;               // inner node AABB (w of lo = subtree SAH cost, w of hi = area)
             int    *flags;                 // arrival counters
+            float  *dpc;                   // collapse DP: C(n,1..7), 7 floats per inner node
+            unsigned char *dpk;            // collapse DP: best left budget for j = 2..8 at [j-1], 8 bytes per inner node
         };
 
         __global__ void k_prim_bounds(const float *__restrict__ wv, uint32_t n, float4 *__restrict__ plo, float4 *__restrict__ phi, int *bounds)
@@ -130,7 +132,6 @@ namespace crb
             const int lref = (lo == gamma) ? ~gamma : gamma;
             const int rref = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
             t.left[i] = lref, t.right[i] = rref;
-            t.first[i] = lo, t.last[i] = hi;
             if (lref < 0) t.leaf_parent[~lref] = i; else t.parent[lref] = i;
             if (rref < 0) t.leaf_parent[~rref] = i; else t.parent[rref] = i;
             if (i == 0) t.parent[0] = -1;
@@ -181,7 +182,8 @@ namespace crb
                 const float area = box_area(lo, hi);
                 // SAH cost of the subtree: either an inner node over both children, or (small subtrees)
                 // a flat leaf of all its triangles
-                const int   cnt   = t.last[node] - t.first[node] + 1;
+                const int   cnt   = (t.left[node] < 0 ? 1 : t.count[t.left[node]]) + (t.right[node] < 0 ? 1 : t.count[t.right[node]]);
+                t.count[node]     = cnt;
                 float       cost  = SAH_CI * area + ca + cb;
                 const float cleaf = SAH_CT * area * float(cnt);
                 if (cnt <= BVH8_LEAF_TRIS && cleaf < cost) cost = cleaf;
@@ -192,6 +194,65 @@ namespace crb
         }
 
         // ------------------------------------------------------------------ K4 collapse
+        // Cost tables for the SAH-optimal binary -> 8-wide collapse (the dynamic programme of Ylitie,
+        // Karras & Laine 2017 §4, as published): C(n,i) = cheapest way to represent the binary subtree n as
+        // at most i children of one wide node.
+        //   C(n,1) = leaf cost A(n) P(n) c_prim           if P(n) <= 3
+        //          = A(n) c_node + D(n,8)                  otherwise (n becomes a wide node)
+        //   C(n,i) = min(D(n,i), C(n,i-1)),  D(n,j) = min_{0<k<j} C(left,k) + C(right,j-k)
+        // c_node : c_prim follows the measured instruction cost of a node test vs a triangle test (~3:1).
+        constexpr float DP_CNODE = 1.0f, DP_CPRIM = 0.35f;
+
+        __global__ void k_collapse_dp(int n, BinTree t, const float4 *__restrict__ plo, const float4 *__restrict__ phi, const uint32_t *__restrict__ vals)
+        {
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            int node = t.leaf_parent[i];
+            while (node >= 0)
+            {
+                __threadfence();
+                if (atomicAdd(t.flags + node, 1) == 0) return;
+                __threadfence();
+                float cl[8], cr[8];
+                for (int side = 0; side < 2; side++)
+                {
+                    const int ref = side ? t.right[node] : t.left[node];
+                    float    *dst = side ? cr : cl;
+                    if (ref < 0)
+                    {
+                        const uint32_t p = vals[~ref];
+                        const float    a = box_area(plo[p], phi[p]) * DP_CPRIM;
+                        for (int k = 1; k < 8; k++) dst[k] = a;
+                    }
+                    else
+                        for (int k = 1; k < 8; k++) dst[k] = t.dpc[size_t(ref) * 7 + (k - 1)];
+                }
+                float         dist[9];
+                unsigned char kb[9];
+                for (int j = 2; j <= 8; j++)
+                {
+                    float best = 3e38f;
+                    int   bk   = 1;
+                    for (int k = 1; k < j; k++)
+                    {
+                        if (k > 7 || j - k > 7) continue;
+                        const float c = cl[k] + cr[j - k];
+                        if (c < best) best = c, bk = k;
+                    }
+                    dist[j] = best, kb[j] = (unsigned char) bk;
+                }
+                const float area = t.hi[node].w;
+                const int   cnt  = t.count[node];
+                float      *out  = t.dpc + size_t(node) * 7;
+                out[0]           = cnt <= BVH8_LEAF_TRIS ? area * float(cnt) * DP_CPRIM : area * DP_CNODE + dist[8];
+                for (int k = 2; k <= 7; k++) out[k - 1] = fminf(dist[k], out[k - 2]);
+                unsigned char *ko = t.dpk + size_t(node) * 8;
+                ko[0]             = 0;
+                for (int j = 2; j <= 8; j++) ko[j - 1] = kb[j];
+                node = t.parent[node];
+            }
+        }
+
         struct CollapseCtx
         {
             BinTree         t;
@@ -203,10 +264,25 @@ namespace crb
             uint32_t       *counters;    // [0] nodes allocated, [1] tris allocated, [2] out-queue size
             float          *sah;         // accumulated wide-tree SAH cost (area-weighted), informational
             float           root_area;
+            int             use_dp;
         };
 
-        __device__ __forceinline__ int ref_count(const BinTree &t, int ref) { return ref < 0 ? 1 : t.last[ref] - t.first[ref] + 1; }
-        __device__ __forceinline__ int ref_first(const BinTree &t, int ref) { return ref < 0 ? ~ref : t.first[ref]; }
+        __device__ __forceinline__ int ref_count(const BinTree &t, int ref) { return ref < 0 ? 1 : t.count[ref]; }
+        // sorted positions of the (<= BVH8_LEAF_TRIS) leaves below ref, left to right
+        __device__ __forceinline__ int ref_leaves(const BinTree &t, int ref, int *out)
+        {
+            int n = 0, sp = 0, stack[BVH8_LEAF_TRIS + 1];
+            stack[sp++] = ref;
+            while (sp)
+            {
+                const int r = stack[--sp];
+                if (r < 0)
+                    out[n++] = ~r;
+                else
+                    stack[sp++] = t.right[r], stack[sp++] = t.left[r];
+            }
+            return n;
+        }
 
         __global__ void k_collapse(CollapseCtx c, const uint2 *__restrict__ in, uint32_t n_in, uint2 *__restrict__ out)
         {
@@ -221,21 +297,56 @@ namespace crb
                 ch[0] = c.t.left[root], ch[1] = c.t.right[root], k = 2;
             else
                 ch[0] = root, k = 1;
-            // greedy expansion: open the inner child with the largest surface area until 8 children
-            while (k < 8)
+            if (c.use_dp && root >= 0)
             {
-                int   best  = -1;
-                float besta = -1.f;
-                for (int j = 0; j < k; j++)
-                    if (ch[j] >= 0)
+                // SAH-optimal choice of the (at most 8) children from the DP tables of k_collapse_dp:
+                // distribute 8 slots over the two binary children, recursively, until a budget of one slot
+                // (or a budget whose extra slots buy nothing) turns a binary subtree into a child.
+                int sref[16], sbud[16], sp = 0;
+                k                = 0;
+                const int k8     = c.t.dpk[size_t(root) * 8 + 7];
+                sref[sp] = c.t.right[root], sbud[sp] = 8 - k8, sp++;
+                sref[sp] = c.t.left[root], sbud[sp] = k8, sp++;
+                while (sp)
+                {
+                    --sp;
+                    const int m = sref[sp];
+                    int       j = sbud[sp];
+                    if (m < 0)
                     {
-                        const float a = c.t.hi[ch[j]].w;
-                        if (a > besta) besta = a, best = j;
+                        ch[k++] = m;
+                        continue;
                     }
-                if (best < 0) break;
-                const int r = ch[best];
-                ch[best]    = c.t.left[r];
-                ch[k++]     = c.t.right[r];
+                    const float *cm = c.t.dpc + size_t(m) * 7;
+                    while (j > 1 && cm[j - 1] >= cm[j - 2]) j--;    // C(m,j) == C(m,j-1): the extra slot is useless
+                    if (j == 1)
+                    {
+                        ch[k++] = m;
+                        continue;
+                    }
+                    const int kl = c.t.dpk[size_t(m) * 8 + (j - 1)];
+                    sref[sp] = c.t.right[m], sbud[sp] = j - kl, sp++;
+                    sref[sp] = c.t.left[m], sbud[sp] = kl, sp++;
+                }
+            }
+            else
+            {
+                // greedy fallback: open the inner child with the largest surface area until 8 children
+                while (k < 8)
+                {
+                    int   best  = -1;
+                    float besta = -1.f;
+                    for (int j = 0; j < k; j++)
+                        if (ch[j] >= 0)
+                        {
+                            const float a = c.t.hi[ch[j]].w;
+                            if (a > besta) besta = a, best = j;
+                        }
+                    if (best < 0) break;
+                    const int r = ch[best];
+                    ch[best]    = c.t.left[r];
+                    ch[k++]     = c.t.right[r];
+                }
             }
 
             float4 clo[8], chi[8];
@@ -330,10 +441,11 @@ namespace crb
                 if (cnt <= BVH8_LEAF_TRIS)
                 {
                     meta[s]         = (((1u << cnt) - 1u) << 5) | unsigned(tri_off);
-                    const int first = ref_first(c.t, ch[j]);
+                    int leaves[BVH8_LEAF_TRIS];
+                    ref_leaves(c.t, ch[j], leaves);
                     for (int q = 0; q < cnt; q++)
                     {
-                        const uint32_t prim = c.vals[first + q];
+                        const uint32_t prim = c.vals[leaves[q]];
                         const float   *v    = c.wv + size_t(prim) * 9;
                         float4        *dst  = c.tris + size_t(tri_base + uint32_t(tri_off + q)) * 3;
                         dst[0]              = make_float4(v[0], v[1], v[2], __uint_as_float(prim));
@@ -413,7 +525,7 @@ namespace crb
         sz(n, 16), sz(n, 16);                 // plo, phi
         sz(8, 4);                             // bounds
         sz(n, 8), sz(n, 8), sz(n, 4), sz(n, 4);    // keys x2, vals x2
-        sz(ni, 4), sz(ni, 4), sz(ni, 4), sz(n, 4), sz(ni, 4), sz(ni, 4), sz(ni, 16), sz(ni, 16), sz(ni, 4);    // tree
+        sz(ni, 4), sz(ni, 4), sz(ni, 4), sz(n, 4), sz(ni, 4), sz(ni, 16), sz(ni, 16), sz(ni, 4), sz(ni, 28), sz(ni, 8);    // tree + collapse DP tables
         sz(max_nodes, 8), sz(max_nodes, 8);   // collapse queues
         sz(8, 4);                             // counters + sah
         DBuf<char> scratch;
@@ -425,9 +537,11 @@ namespace crb
         uint32_t *vals0 = carve<uint32_t>(p, n), *vals1 = carve<uint32_t>(p, n);
         BinTree   t;
         t.left = carve<int>(p, ni), t.right = carve<int>(p, ni), t.parent = carve<int>(p, ni), t.leaf_parent = carve<int>(p, n);
-        t.first = carve<int>(p, ni), t.last = carve<int>(p, ni);
+        t.count = carve<int>(p, ni);
         t.lo = carve<float4>(p, ni), t.hi = carve<float4>(p, ni);
         t.flags      = carve<int>(p, ni);
+        t.dpc        = carve<float>(p, ni * 7);
+        t.dpk        = carve<unsigned char>(p, ni * 8);
         uint2    *q0 = carve<uint2>(p, max_nodes), *q1 = carve<uint2>(p, max_nodes);
         uint32_t *counters = carve<uint32_t>(p, 8);
 
@@ -474,7 +588,12 @@ namespace crb
             CRB_LAUNCH(k_hierarchy, (unsigned(ni) + B - 1) / B, B, stream, keys, int(n), t);
             CRB_LAUNCH(k_refit, gn, B, stream, int(n), t, plo, phi, vals);
             // ---- K3
-            if (opt.treelets && n >= 16) treelet_optimize(t, int(n), plo, phi, vals, stream);
+            if (opt.treelet_passes > 0 && n >= 16)
+            {
+                dev_zero(counters + 5, 4, stream);
+                treelet_optimize(t, int(n), plo, phi, vals, stream, opt.treelet_passes, counters + 5);
+                dev_download(&stats.treelets_changed, counters + 5, 4, stream);
+            }
             float4 hi0;
             dev_download(&hi0, t.hi, sizeof(float4), stream);
             root_area = hi0.w;
@@ -491,6 +610,12 @@ namespace crb
         CollapseCtx c;
         c.t = t, c.plo = plo, c.phi = phi, c.vals = vals, c.wv = d_wverts, c.nodes = nodes.p, c.tris = tris.p;
         c.counters = counters, c.sah = reinterpret_cast<float *>(counters + 4), c.root_area = root_area;
+        c.use_dp = (opt.optimal_collapse && n > 1) ? 1 : 0;
+        if (c.use_dp)
+        {
+            dev_zero(t.flags, ni * sizeof(int), stream);
+            CRB_LAUNCH(k_collapse_dp, gn, B, stream, int(n), t, plo, phi, vals);
+        }
         uint32_t n_in  = 1;
         uint32_t depth = 0;
         uint2   *qin = q0, *qout = q1;

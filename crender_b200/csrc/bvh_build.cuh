@@ -13,11 +13,13 @@ namespace crb
         uint32_t n_tris    = 0;
         uint32_t max_depth = 0;
         float    sah_cost  = 0;
+        uint32_t treelets_changed = 0;
     };
 
     struct BuildOptions
     {
-        bool treelets = true;    // SAH treelet restructuring passes on the binary tree before collapse
+        int  treelet_passes = 2;       // SAH treelet restructuring sweeps over the binary tree before the collapse
+        bool optimal_collapse = true;  // SAH-optimal (dynamic programming) binary -> 8-wide collapse; false = greedy by area
     };
 
     // wverts: device pointer, 9 floats per triangle (world space), n triangles.

@@ -193,6 +193,8 @@ inline T __shfl_down_sync(unsigned, T v, int)
     return v;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline void __syncthreads() {}    // emulated launches use one thread per block
+#define __shared__ static
 inline void __threadfence() {}
 template<typename T>
 inline T __ldg(const T *p)

@@ -65,6 +65,38 @@ namespace crb
             base = __shfl_sync(0xffffffffu, base, leader);
             return base + uint32_t(__popc(mask & ((1u << crb_lane_id()) - 1u)));
         }
+        // Block-aggregated reservation of queue space in NQ queues at once: warps count with a ballot, add
+        // into shared memory, and ONE thread per queue issues the global atomic for the whole block
+        // (same-address global atomics serialise in L2; per-warp pushes of a full-frame wavefront are
+        // hundreds of thousands of them). Must be called by every thread of the block.
+        template<int NQ>
+        __device__ __forceinline__ void block_reserve(const bool (&pred)[NQ], uint32_t *counters, const int (&cidx)[NQ], uint32_t (&at)[NQ])
+        {
+            __shared__ uint32_t s_cnt[NQ], s_base[NQ];
+            const unsigned lane = crb_lane_id();
+            for (int q = threadIdx.x; q < NQ; q += blockDim.x) s_cnt[q] = 0;
+            __syncthreads();
+            uint32_t woff[NQ];
+            unsigned mask[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+            {
+                mask[q] = __ballot_sync(0xffffffffu, pred[q]);
+                woff[q] = 0;
+                if (mask[q])
+                {
+                    if (lane == 0) woff[q] = atomicAdd(&s_cnt[q], uint32_t(__popc(mask[q])));
+                    woff[q] = __shfl_sync(0xffffffffu, woff[q], 0);
+                }
+            }
+            __syncthreads();
+            for (int q = threadIdx.x; q < NQ; q += blockDim.x)
+                if (s_cnt[q]) s_base[q] = atomicAdd(counters + cidx[q], s_cnt[q]);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < NQ; q++) at[q] = s_base[q] + woff[q] + uint32_t(__popc(mask[q] & ((1u << lane) - 1u)));
+        }
+
         // persistent work fetch: a warp takes CRB_WARP consecutive items at a time
         __device__ __forceinline__ uint32_t warp_fetch(uint32_t *cursor)
         {
@@ -146,45 +178,64 @@ namespace crb
         }
 
         // ------------------------------------------------------------------ trace + material sort
-        template<bool COUNT>
-        __global__ void __launch_bounds__(256) k_trace(DScene sc, PathState ps)
+        constexpr int TRACE_STEPS = 4;    // node iterations between two refill points of the persistent trace loop
+
+        template<bool COUNT, int STEPS>
+        __global__ void __launch_bounds__(256, 4) k_trace(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_IN];
             TravCounters   tc;
-            for (;;)
-            {
-                const uint32_t base = warp_fetch(ps.counters + CTR_CUR_TRACE);
-                if (base >= n) break;
-                const uint32_t idx = base + crb_lane_id();
-                int            cls  = -1;
-                uint32_t       slot = 0;
-                if (idx < n)
-                {
-                    slot           = ps.q_in[idx];
-                    const float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
-                    // model.cpp:107-112: the query direction is normalised; tnear/tfar of model.cpp:21-22
-                    const V3  dn = normalize(v3(d.x, d.y, d.z));
-                    const Hit h  = traverse<false, COUNT>(sc.bvh, v3(o.x, o.y, o.z), dn, 0.00001f, inf_f(), &tc);
-                    ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-                    if (h.prim == INVALID_PRIM)
-                        cls = 0;
-                    else
-                    {
-                        const uint32_t mat = __float_as_uint(__ldg(sc.shade_tri + src_tri(sc, h.prim)).w);
-                        cls                = 1 + int(sc.materials[mat].shade_type);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 4; c++)
-                {
-                    const uint32_t at = warp_push(ps.counters + CTR_CLASS0 + c, cls == c);
-                    if (cls == c) ps.q_class[c][at] = slot;
-                }
-            }
+            auto source = [&](uint32_t idx, uint32_t &slot, V3 &o, V3 &d, float &tmin, float &tmax) {
+                slot             = ps.q_in[idx];
+                const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                o               = v3(ro.x, ro.y, ro.z);
+                d               = normalize(v3(rd.x, rd.y, rd.z));    // model.cpp:107-112: the query direction is normalised
+                tmin = 0.00001f, tmax = inf_f();                      // model.cpp:21-22
+            };
+            // retiring a ray is one 16-byte store; the material sort is a separate full-width pass
+            // (k_classify) because only a few lanes of a warp retire at any refill point
+            auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
+                if (valid) ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            };
+            trace_persistent<false, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_TRACE, n, ps.trace_chunk, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES, tc.nodes);
                 atomicAdd(ps.stats + ST_TRIS, tc.tris);
+            }
+        }
+
+        // material sort: every traced path is pushed to the queue of its shade class (0 miss, 1 metal,
+        // 2 smooth, 3 glass) with one warp-aggregated atomic per class per warp
+        __global__ void __launch_bounds__(256) k_classify(DScene sc, PathState ps)
+        {
+            const uint32_t n = ps.counters[CTR_IN];
+            // all threads of a block iterate together (the reservation is block-collective)
+            for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
+            {
+                const uint32_t idx  = tile + threadIdx.x;
+                int            cls  = -1;
+                uint32_t       slot = 0;
+                if (idx < n)
+                {
+                    slot                = ps.q_in[idx];
+                    const uint32_t prim = __float_as_uint(ps.hit[slot].w);
+                    if (prim == INVALID_PRIM)
+                        cls = 0;
+                    else
+                    {
+                        const uint32_t mat = __float_as_uint(__ldg(sc.shade_tri + src_tri(sc, prim)).w);
+                        cls                = 1 + int(sc.materials[mat].shade_type);
+                    }
+                }
+                const bool pred[4] = { cls == 0, cls == 1, cls == 2, cls == 3 };
+                const int  cidx[4] = { CTR_CLASS0, CTR_CLASS0 + 1, CTR_CLASS0 + 2, CTR_CLASS0 + 3 };
+                uint32_t   at[4];
+                block_reserve<4>(pred, ps.counters, cidx, at);
+                if (cls == 0) ps.q_class[0][at[0]] = slot;
+                if (cls == 1) ps.q_class[1][at[1]] = slot;
+                if (cls == 2) ps.q_class[2][at[2]] = slot;
+                if (cls == 3) ps.q_class[3][at[3]] = slot;
             }
         }
 
@@ -252,11 +303,9 @@ namespace crb
             const uint32_t c0 = ps.counters[CTR_CLASS0], c1 = c0 + ps.counters[CTR_CLASS0 + 1], c2 = c1 + ps.counters[CTR_CLASS0 + 2],
                            n = c2 + ps.counters[CTR_CLASS0 + 3];
             const uint32_t i = rp.bounce;
-            for (;;)
+            for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
             {
-                const uint32_t base = warp_fetch(ps.counters + CTR_CUR_SHADE);
-                if (base >= n) break;
-                const uint32_t idx      = base + crb_lane_id();
+                const uint32_t idx      = tile + threadIdx.x;
                 bool           survive  = false, want_shadow = false;
                 uint32_t       slot     = 0;
                 ShadowRay      sr;
@@ -381,16 +430,51 @@ namespace crb
                         }
                     }
                 }
-                const uint32_t at = warp_push(ps.counters + CTR_NEXT, survive);
-                if (survive) ps.q_next[at] = slot;
-                const uint32_t sat = warp_push(ps.counters + CTR_SHADOW, want_shadow);
-                if (want_shadow) ps.shadow[sat] = sr;
+                const bool pred[2] = { survive, want_shadow };
+                const int  cidx[2] = { CTR_NEXT, CTR_SHADOW };
+                uint32_t   at[2];
+                block_reserve<2>(pred, ps.counters, cidx, at);
+                if (survive) ps.q_next[at[0]] = slot;
+                if (want_shadow) ps.shadow[at[1]] = sr;
             }
         }
 
         // ------------------------------------------------------------------ K8 shadow rays
+        // sun visibility without alpha cut-outs: any-hit through the persistent trace loop
+        template<bool COUNT, int STEPS>
+        __global__ void __launch_bounds__(256, 4) k_shadow(DScene sc, PathState ps)
+        {
+            const uint32_t n = ps.counters[CTR_SHADOW];
+            TravCounters   tc;
+            auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
+                item            = idx;
+                const float4 so = ps.shadow[idx].o, sd = ps.shadow[idx].d;
+                o               = v3(so.x, so.y, so.z);
+                d               = normalize(v3(sd.x, sd.y, sd.z));    // model.cpp:110-112
+                tmin = 0.00001f, tmax = inf_f();
+            };
+            auto sink = [&](bool valid, uint32_t item, const Hit &h) {
+                if (valid && h.prim == INVALID_PRIM)
+                {
+                    // renderer.cpp:348-353: the sun is visible, connect
+                    const uint32_t slot = __float_as_uint(ps.shadow[item].o.w);
+                    const float4   c    = ps.shadow[item].c;
+                    const float4   r4   = ps.rad[slot];
+                    const V3       r    = v3(r4.x, r4.y, r4.z) + v3(c.x, c.y, c.z);
+                    ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
+                }
+            };
+            trace_persistent<true, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_SHADOW, n, ps.trace_chunk, source, sink, &tc);
+            if (COUNT)
+            {
+                atomicAdd(ps.stats + ST_NODES_SHADOW, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS_SHADOW, tc.tris);
+            }
+        }
+
+        // sun visibility with alpha cut-outs present: the reference's closest-hit march (renderer.cpp:330-345)
         template<bool COUNT>
-        __global__ void __launch_bounds__(256) k_shadow(DScene sc, PathState ps)
+        __global__ void __launch_bounds__(256) k_shadow_alpha(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_SHADOW];
             TravCounters   tc;
@@ -405,26 +489,19 @@ namespace crb
                     V3              o  = v3(sr.o.x, sr.o.y, sr.o.z);
                     const V3        d  = v3(sr.d.x, sr.d.y, sr.d.z);
                     const V3        dn = normalize(d);    // model.cpp:110-112
-                    bool            visible;
-                    if (!sc.has_alpha)
-                        visible = traverse<true, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), &tc).prim == INVALID_PRIM;
-                    else
+                    bool            visible = false;
+                    for (int guard = 0; guard < 4096; guard++)
                     {
-                        // renderer.cpp:330-345: closest hit, marching through alpha cut-outs in 0.1 steps
-                        visible = false;
-                        for (int guard = 0; guard < 4096; guard++)
+                        const Hit h = traverse<false, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), &tc);
+                        if (h.prim == INVALID_PRIM)
                         {
-                            const Hit h = traverse<false, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), &tc);
-                            if (h.prim == INVALID_PRIM)
-                            {
-                                visible = true;
-                                break;
-                            }
-                            const Surface   sf  = surface_at(sc, o, dn, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
-                            const DMaterial mat = sc.materials[sf.mat];
-                            if (surface_colour(sc, mat, sf).w != 0.0f) break;
-                            o = sf.point + d * 0.1f;
+                            visible = true;
+                            break;
                         }
+                        const Surface   sf  = surface_at(sc, o, dn, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
+                        const DMaterial mat = sc.materials[sf.mat];
+                        if (surface_colour(sc, mat, sf).w != 0.0f) break;
+                        o = sf.point + d * 0.1f;    // marches in 0.1 steps of the un-normalised direction
                     }
                     if (visible)
                     {
@@ -658,6 +735,8 @@ namespace crb
         ps.q_in = q_in.p, ps.q_next = q_next.p;
         for (int c = 0; c < 4; c++) ps.q_class[c] = q_class[c].p;
         ps.shadow = shadow.p, ps.counters = counters.p, ps.stats = dstats.p;
+        static const uint32_t trace_chunk = getenv("CRB_TRACE_CHUNK") ? uint32_t(atoi(getenv("CRB_TRACE_CHUNK"))) : 0u;    // tuning knob
+        ps.trace_chunk = trace_chunk;
 
         RenderParams rp {};
         rp.w = w, rp.h = h, rp.row0 = row0, rp.nrows = nrows, rp.npix = npix, rp.seed = seed;
@@ -665,6 +744,7 @@ namespace crb
         rp.accum = accum.p, rp.display = display.p, rp.albedo = albedo.p, rp.normal = normal.p, rp.depth = depth.p;
 
         const bool count = (flags & CRB_RENDER_FLAG_COUNTERS) != 0;
+        static const int steps = getenv("CRB_TRACE_STEPS") ? atoi(getenv("CRB_TRACE_STEPS")) : TRACE_STEPS;    // tuning knob
 #ifdef CRB_EMU
         const unsigned pgrid = 1, pblock = 1;
 #else
@@ -694,21 +774,41 @@ namespace crb
                 rp.bounce = i;
                 tick(CRB_K_TRACE);
                 if (count)
-                    CRB_LAUNCH((k_trace<true>), pgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<true, TRACE_STEPS>), pgrid, pblock, st, dscene, ps);
+                else if (steps == 1)
+                    CRB_LAUNCH((k_trace<false, 1>), pgrid, pblock, st, dscene, ps);
+                else if (steps == 2)
+                    CRB_LAUNCH((k_trace<false, 2>), pgrid, pblock, st, dscene, ps);
+                else if (steps == 8)
+                    CRB_LAUNCH((k_trace<false, 8>), pgrid, pblock, st, dscene, ps);
                 else
-                    CRB_LAUNCH((k_trace<false>), pgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 4>), pgrid, pblock, st, dscene, ps);
                 tock();
                 tick(CRB_K_SHADE);
+                CRB_LAUNCH(k_classify, pgrid, pblock, st, dscene, ps);
                 CRB_LAUNCH(k_shade, pgrid, pblock, st, dscene, rp, ps);
                 tock();
-                launches += 2;
+                launches += 3;
                 if (dscene.sun.enabled)
                 {
                     tick(CRB_K_SHADOW);
-                    if (count)
-                        CRB_LAUNCH((k_shadow<true>), pgrid, pblock, st, dscene, ps);
+                    if (dscene.has_alpha)
+                    {
+                        if (count)
+                            CRB_LAUNCH((k_shadow_alpha<true>), pgrid, pblock, st, dscene, ps);
+                        else
+                            CRB_LAUNCH((k_shadow_alpha<false>), pgrid, pblock, st, dscene, ps);
+                    }
+                    else if (count)
+                        CRB_LAUNCH((k_shadow<true, TRACE_STEPS>), pgrid, pblock, st, dscene, ps);
+                    else if (steps == 1)
+                        CRB_LAUNCH((k_shadow<false, 1>), pgrid, pblock, st, dscene, ps);
+                    else if (steps == 2)
+                        CRB_LAUNCH((k_shadow<false, 2>), pgrid, pblock, st, dscene, ps);
+                    else if (steps == 8)
+                        CRB_LAUNCH((k_shadow<false, 8>), pgrid, pblock, st, dscene, ps);
                     else
-                        CRB_LAUNCH((k_shadow<false>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 4>), pgrid, pblock, st, dscene, ps);
                     tock();
                     launches++;
                 }

@@ -91,6 +91,7 @@ namespace crb
         if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
             throw Error(ERR_NO_DEVICE, "no CUDA device: crender_b200 has no CPU path");
         CRB_CUDA_CHECK(cudaGetDevice(&device));
+        CRB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
         CRB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 #endif
         // components.h:23-29
@@ -306,6 +307,8 @@ namespace crb
 
         // ---- BVH
         BuildOptions opt;
+        if (const char *e = getenv("CRB_TREELET_PASSES")) opt.treelet_passes = atoi(e);    // build-quality experiments
+        if (const char *e = getenv("CRB_OPTIMAL_COLLAPSE")) opt.optimal_collapse = atoi(e) != 0;
         build_bvh8(d_wverts.p, n_flat, stream, opt, d_nodes, d_tris, build);
         d_wverts.release();
         committed = true;

@@ -96,6 +96,7 @@ namespace crb
     struct Scene
     {
         int          device = 0;
+        int          n_sms  = 1;
         cudaStream_t stream = nullptr;
 
         std::vector<HostModel>   models;

@@ -24,25 +24,28 @@ namespace crb
             prim = flat - r.start, model = r.model, inst = r.inst;
         }
 
+        constexpr int BATCH_STEPS = 4;
+
+        // persistent kernels: each warp is a pool of 32 traversal lanes refilled from `cursor` (bvh8.cuh)
         template<bool COUNT>
-        __global__ void __launch_bounds__(256) k_intersect_batch(DScene sc, const float4 *__restrict__ rays, uint64_t n, crb_hit *__restrict__ hits,
-                                                                 unsigned long long *ctr)
+        __global__ void __launch_bounds__(256, 4) k_intersect_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits,
+                                                                 uint32_t *cursor, unsigned long long *ctr)
         {
-            const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-            TravCounters   tc;
-            if (i < n)
-            {
-                const float4 a = rays[2 * i], b = rays[2 * i + 1];
-                const Hit    h = traverse<false, COUNT>(sc.bvh, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, b.w, &tc);
-                if (!COUNT)
-                {
-                    crb_hit out;
-                    out.t = h.t, out.u = h.u, out.v = h.v;
-                    out.prim = INVALID_PRIM, out.model = INVALID_PRIM, out.inst = 0;
-                    if (h.prim != INVALID_PRIM) resolve_flat(sc, h.prim, out.prim, out.model, out.inst);
-                    hits[i] = out;
-                }
-            }
+            TravCounters tc;
+            auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
+                item           = idx;
+                const float4 a = rays[2 * size_t(idx)], b = rays[2 * size_t(idx) + 1];
+                o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z), tmin = a.w, tmax = b.w;
+            };
+            auto sink = [&](bool valid, uint32_t item, const Hit &h) {
+                if (COUNT || !valid) return;
+                crb_hit out;
+                out.t = h.t, out.u = h.u, out.v = h.v;
+                out.prim = INVALID_PRIM, out.model = INVALID_PRIM, out.inst = 0;
+                if (h.prim != INVALID_PRIM) resolve_flat(sc, h.prim, out.prim, out.model, out.inst);
+                hits[item] = out;
+            };
+            trace_persistent<false, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ctr + 0, tc.nodes);
@@ -51,17 +54,19 @@ namespace crb
         }
 
         template<bool COUNT>
-        __global__ void __launch_bounds__(256) k_occluded_batch(DScene sc, const float4 *__restrict__ rays, uint64_t n, uint8_t *__restrict__ occ,
-                                                                unsigned long long *ctr)
+        __global__ void __launch_bounds__(256, 4) k_occluded_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, uint8_t *__restrict__ occ,
+                                                                uint32_t *cursor, unsigned long long *ctr)
         {
-            const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-            TravCounters   tc;
-            if (i < n)
-            {
-                const float4 a = rays[2 * i], b = rays[2 * i + 1];
-                const Hit    h = traverse<true, COUNT>(sc.bvh, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, b.w, &tc);
-                if (!COUNT) occ[i] = h.prim != INVALID_PRIM ? 1 : 0;
-            }
+            TravCounters tc;
+            auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
+                item           = idx;
+                const float4 a = rays[2 * size_t(idx)], b = rays[2 * size_t(idx) + 1];
+                o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z), tmin = a.w, tmax = b.w;
+            };
+            auto sink = [&](bool valid, uint32_t item, const Hit &h) {
+                if (!COUNT && valid) occ[item] = h.prim != INVALID_PRIM ? 1 : 0;
+            };
+            trace_persistent<true, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ctr + 0, tc.nodes);
@@ -113,6 +118,8 @@ namespace crb
             DBuf<unsigned long long> d_ctr;
             d_ctr.alloc(2);
             dev_zero(d_ctr.p, 16, s.stream);
+            DBuf<uint32_t> d_cursor;
+            d_cursor.alloc(1);
             const size_t out_elem = mode == 0 ? sizeof(crb_hit) : 1;
             DBuf<float4> d_rays;
             DBuf<char>   d_out;
@@ -134,14 +141,20 @@ namespace crb
                     dev_upload(d_rays.p, rays + off, cnt * sizeof(crb_ray), s.stream);
                     rp = d_rays.p, op = d_out.p;
                 }
-                const unsigned g = unsigned((cnt + B - 1) / B);
+#ifdef CRB_EMU
+                const unsigned g = 1, blk = 1;
+#else
+                const unsigned g = unsigned(s.n_sms) * 4, blk = B;
+#endif
+                const uint32_t cnt32 = uint32_t(cnt);
+                dev_zero(d_cursor.p, 4, s.stream);
                 timer.start();
                 switch (mode)
                 {
-                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, B, s.stream, sc, rp, cnt, reinterpret_cast<crb_hit *>(op), d_ctr.p); break;
-                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, B, s.stream, sc, rp, cnt, reinterpret_cast<uint8_t *>(op), d_ctr.p); break;
-                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, B, s.stream, sc, rp, cnt, (crb_hit *) nullptr, d_ctr.p); break;
-                default: CRB_LAUNCH((k_occluded_batch<true>), g, B, s.stream, sc, rp, cnt, (uint8_t *) nullptr, d_ctr.p); break;
+                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), d_cursor.p, d_ctr.p); break;
+                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<uint8_t *>(op), d_cursor.p, d_ctr.p); break;
+                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, blk, s.stream, sc, rp, cnt32, (crb_hit *) nullptr, d_cursor.p, d_ctr.p); break;
+                default: CRB_LAUNCH((k_occluded_batch<true>), g, blk, s.stream, sc, rp, cnt32, (uint8_t *) nullptr, d_cursor.p, d_ctr.p); break;
                 }
                 ms += timer.stop();
                 if (!on_device && mode < 2) dev_download(static_cast<char *>(out) + off * out_elem, d_out.p, cnt * out_elem, s.stream);
