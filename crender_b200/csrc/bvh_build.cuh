@@ -18,7 +18,7 @@ namespace crb
 
     struct BuildOptions
     {
-        int  treelet_passes = 2;       // SAH treelet restructuring sweeps over the binary tree before the collapse
+        int  treelet_passes = 1;       // SAH treelet restructuring sweeps (a second sweep buys <0.5 % rays/s for +11 ms at 1M triangles)
         bool optimal_collapse = true;  // SAH-optimal (dynamic programming) binary -> 8-wide collapse; false = greedy by area
     };
 

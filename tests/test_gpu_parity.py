@@ -144,3 +144,26 @@ def test_1m_render_rows_vs_oracle(oracle, big):
     b = ro.raw_sum()[h - y1 : h - y0, :, :3]
     assert b.mean() > 0
     assert common.relrmse(a, b) <= pc.IMG_RELRMSE
+
+
+def test_cpp_host_mirror_cli_matches_python_api(product_lib, tmp_path):
+    # crender_b200/host/crender.hpp (the C++ mirror of cr::scene / cr::renderer) through its headless driver
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "crender_b200", "host", "crender_cli")
+    assert os.path.exists(cli), "crender_cli missing: run __graft_entry__.build()"
+    out = tmp_path / "cornell.bin"
+    subprocess.run([cli, str(out), "96", "80", "8", "6", "5"], check=True)
+    raw = np.fromfile(out, dtype=np.uint8)
+    w, h = np.frombuffer(raw[:8], dtype=np.int32)
+    img = np.frombuffer(raw[8:], dtype=np.float32).reshape(h, w, 4)
+    g = api.scene(lib_path=product_lib)
+    scenes.load(scenes.cornell(), g)
+    g.commit()
+    r = api.renderer(96, 80, 6, g, seed=5)
+    r.render(8)
+    ref = r.current_progress()
+    # same library, same geometry (the CLI indexes its quads, the Python scene is a soup): identical floats
+    assert common.relrmse(img[..., :3], ref[..., :3]) < 1e-6
