@@ -63,14 +63,21 @@ def accum_tensor(rend):
     return torch.as_tensor(_DevicePtr(ptr, n), device="cuda")
 
 
-def merge_renderer(rend, partition: str = "spp") -> int:
-    """Merge the accumulation buffers of all ranks into every rank's renderer and re-resolve."""
+def merge_renderer(rend, partition: str = "spp", passes_local=None) -> int:
+    """Merge the accumulation buffers of all ranks into every rank's renderer and re-resolve.
+    passes_local: passes this rank rendered per pixel. Defaults to the renderer's own counter, which is
+    right for the spp partition; with the tile partition a rank issues one render call per row band, so the
+    caller states the per-pixel pass count."""
     import torch
 
     rend.sync()
     t = accum_tensor(rend)
     torch.cuda.synchronize()
-    passes = merge_partial_sums(t, rend.current_stats().passes, partition)
+    if passes_local is None:
+        if partition != "spp":
+            raise ValueError("tile partition: pass the per-pixel pass count (passes_local)")
+        passes_local = rend.current_stats().passes
+    passes = merge_partial_sums(t, passes_local, partition)
     torch.cuda.synchronize()
     rend.set_pass_count(passes)
     rend.resolve()
