@@ -91,6 +91,7 @@ SIGNATURES = {
     "crb_occluded_batch": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
     "crb_trace_counters": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "crb_last_query_ms": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "crb_microbench_read": (C.c_int, [_P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "crb_scene_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "crb_render_create": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "crb_render_destroy": (C.c_int, [_P]),

@@ -220,6 +220,12 @@ class scene:
         _capi.check(self._lib, self._lib.crb_trace_counters(self._h, _ptr(r), r.shape[0], 0, int(any_hit), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def microbench_read(self, nbytes: int, iters: int) -> float:
+        """GB/s of 16-byte reads over a working set of nbytes (L2 vs HBM roofline context)."""
+        g = C.c_double(0)
+        _capi.check(self._lib, self._lib.crb_microbench_read(self._h, nbytes, iters, C.byref(g)))
+        return g.value
+
     def last_query_ms(self) -> float:
         ms = C.c_double(0)
         _capi.check(self._lib, self._lib.crb_last_query_ms(self._h, C.byref(ms)))

@@ -77,6 +77,20 @@ namespace crb
 
     __device__ __forceinline__ unsigned byte_of(unsigned w, int i) { return (w >> (8 * i)) & 0xffu; }
 
+    // 16-byte read-only load that the compiler may not sink below later branches: the three loads of a
+    // triangle record must be in flight together (ncu showed the v0 load issued after the det test,
+    // i.e. two serialised L2 round trips per leaf test)
+    __device__ __forceinline__ float4 ldg128_pinned(const float4 *p)
+    {
+#ifdef CRB_EMU
+        return __ldg(p);
+#else
+        float4 v;
+        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+        return v;
+#endif
+    }
+
     // Intersects the ray with the 8 child boxes of one node. Returns the hit bits: bits 24..31 = inner
     // children at their traversal priority, bits 0..23 = leaf triangles (relative to tri_base).
     __device__ __forceinline__ unsigned node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, V3 o, V3 idir,
@@ -108,14 +122,13 @@ namespace crb
                 const float    t0z = fmaf(float(byte_of(nearz, j)), az, bz), t1z = fmaf(float(byte_of(farz, j)), az, bz);
                 const float    tn  = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
                 const float    tf  = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-                if (meta != 0 && tn <= tf * BVH8_BOX_SLACK)
-                {
-                    const int slot = half * 4 + j;
-                    if ((imask >> slot) & 1u)
-                        hits |= 1u << (24 + (slot ^ octinv));
-                    else
-                        hits |= (meta >> 5) << (meta & 31u);
-                }
+                // branch-free: inner children sit at priority bit 24 + (slot ^ octinv), leaves contribute
+                // their unary triangle count at their triangle offset; an empty slot has meta == 0 -> 0 bits
+                const int      slot  = half * 4 + j;
+                const bool     inner = (imask >> slot) & 1u;
+                const unsigned index = inner ? (24u + (unsigned(slot) ^ octinv)) : (meta & 31u);
+                const unsigned bits  = (meta >> 5) << index;
+                hits |= (tn <= tf * BVH8_BOX_SLACK) ? bits : 0u;
             }
         }
         return hits;
@@ -197,7 +210,7 @@ namespace crb
     //   source(idx, item, o, d, tmin, tmax)  loads work item idx (called by the lane that owns it)
     //   sink(valid, item, hit)               called by ALL lanes at a convergent point; valid lanes retire
     template<bool ANY, bool COUNT, int STEPS, typename Source, typename Sink>
-    __device__ __forceinline__ void trace_persistent(const Bvh8 &bvh, uint32_t *cursor, uint32_t n, uint32_t chunk_max, Source source, Sink sink,
+    __device__ __forceinline__ void trace_persistent(const Bvh8 &bvh, uint32_t *cursor, uint32_t n, uint32_t chunk_max, int postpone, Source source, Sink sink,
                                                      TravCounters *ctr)
     {
         const unsigned FULL = 0xffffffffu;
@@ -210,7 +223,7 @@ namespace crb
         unsigned       octinv = 0;
         float          tmin = 0.f;
         Hit            best { 0.f, 0.f, 0.f, INVALID_PRIM };
-        uint2          group = make_uint2(0u, 0u);
+        uint2          group = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
         uint32_t       local_next = 0, local_end = 0;
         // reservation granularity: large enough to keep the cursor atomic rare, small enough that the last
         // ranges are spread over all warps of the grid
@@ -261,6 +274,7 @@ namespace crb
                             idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
                             octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
                             group  = make_uint2(0u, 0x80000000u);
+                            tgroup = make_uint2(0u, 0u);
                             sp     = 0;
                             active = true;
                         }
@@ -272,7 +286,8 @@ namespace crb
 #pragma unroll 1
             for (int it = 0; it < STEPS; it++)
             {
-                if (active)
+                // ---- node phase: lanes without pending triangles visit one node
+                if (active && tgroup.y == 0u)
                 {
                     const int bit = 31 - __clz(int(group.y & 0xff000000u));
                     group.y &= ~(1u << bit);
@@ -285,15 +300,22 @@ namespace crb
                     if (COUNT) ctr->nodes++;
                     const unsigned h = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, best.t);
                     group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
-                    uint2 tgroup     = make_uint2(n1.y, h & 0x00ffffffu);
-                    bool  done       = false;
-
-                    while (tgroup.y)
+                    tgroup           = make_uint2(n1.y, h & 0x00ffffffu);
+                }
+                // ---- triangle phase, postponed until enough lanes have triangles waiting: a leaf test
+                // issued for 2-3 lanes costs the same issue slots as one issued for 16 (measured: the
+                // un-postponed triangle loop was 52 % of k_trace's instructions at 2.7 active lanes)
+                const bool     pending = active && tgroup.y != 0u;
+                const unsigned pm      = __ballot_sync(FULL, pending);
+                const unsigned nm      = __ballot_sync(FULL, active && !pending);
+                if (pm != 0u && (__popc(pm) >= postpone || nm == 0u))
+                {
+                    if (pending)
                     {
                         const int i = __ffs(int(tgroup.y)) - 1;
                         tgroup.y &= tgroup.y - 1;
                         const float4 *tp = bvh.tris + size_t(tgroup.x + unsigned(i)) * 3;
-                        const float4  a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
                         if (COUNT) ctr->tris++;
                         float t, u, v;
                         if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, best.t, t, u, v))
@@ -301,26 +323,28 @@ namespace crb
                             const unsigned prim = __float_as_uint(a.w);
                             if (ANY)
                             {
-                                best = Hit { t, u, v, prim };
-                                done = true;
-                                break;
+                                // any hit ends the query: drop all remaining work, the advance step below
+                                // retires the ray (single retire point for both query kinds)
+                                best     = Hit { t, u, v, prim };
+                                group.y  = 0u;
+                                tgroup.y = 0u;
+                                sp       = 0;
                             }
-                            if (t < best.t || prim < best.prim) best = Hit { t, u, v, prim };
+                            else if (t < best.t || prim < best.prim)
+                                best = Hit { t, u, v, prim };
                         }
                     }
-
-                    if (!done && (group.y & 0xff000000u) == 0)
-                    {
-                        if (sp == 0)
-                            done = true;
-                        else
-                            group = stack[--sp];
-                    }
-                    if (done)
+                }
+                // ---- advance: nothing left in this node group -> pop, or retire the ray
+                if (active && tgroup.y == 0u && (group.y & 0xff000000u) == 0u)
+                {
+                    if (sp == 0)
                     {
                         if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
                         active = false, finished = true;
                     }
+                    else
+                        group = stack[--sp];
                 }
             }
         }

@@ -205,6 +205,14 @@ int crb_trace_counters(crb_scene *s, const crb_ray *rays, uint64_t n, int on_dev
         crb::trace_counters(s->s, rays, n, on_device != 0, any_hit != 0, nodes, tris);
     });
 }
+int crb_microbench_read(crb_scene *s, uint64_t bytes, int iters, double *gb_per_s)
+{
+    return guarded([&] {
+        need(s, "scene");
+        need(gb_per_s, "gb_per_s");
+        *gb_per_s = crb::read_bandwidth_gbs(s->s, size_t(bytes), iters);
+    });
+}
 int crb_last_query_ms(crb_scene *s, double *ms)
 {
     return guarded([&] {

@@ -197,7 +197,7 @@ namespace crb
             auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
                 if (valid) ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
             };
-            trace_persistent<false, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_TRACE, n, ps.trace_chunk, source, sink, &tc);
+            trace_persistent<false, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_TRACE, n, ps.trace_chunk, ps.postpone, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES, tc.nodes);
@@ -464,7 +464,7 @@ namespace crb
                     ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
                 }
             };
-            trace_persistent<true, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_SHADOW, n, ps.trace_chunk, source, sink, &tc);
+            trace_persistent<true, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_SHADOW, n, ps.trace_chunk, ps.postpone, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES_SHADOW, tc.nodes);
@@ -737,6 +737,8 @@ namespace crb
         ps.shadow = shadow.p, ps.counters = counters.p, ps.stats = dstats.p;
         static const uint32_t trace_chunk = getenv("CRB_TRACE_CHUNK") ? uint32_t(atoi(getenv("CRB_TRACE_CHUNK"))) : 0u;    // tuning knob
         ps.trace_chunk = trace_chunk;
+        static const int postpone = getenv("CRB_POSTPONE") ? atoi(getenv("CRB_POSTPONE")) : 1;    // tuning knob; measured best = 1 (profiles/r1c_sweeps.md)
+        ps.postpone = postpone;
 
         RenderParams rp {};
         rp.w = w, rp.h = h, rp.row0 = row0, rp.nrows = nrows, rp.npix = npix, rp.seed = seed;

@@ -146,4 +146,5 @@ namespace crb
     void intersect_batch(Scene &s, const crb_ray *rays, crb_hit *hits, uint64_t n, bool on_device);
     void occluded_batch(Scene &s, const crb_ray *rays, uint8_t *occ, uint64_t n, bool on_device);
     void trace_counters(Scene &s, const crb_ray *rays, uint64_t n, bool on_device, bool any_hit, uint64_t *nodes, uint64_t *tris);
+    double read_bandwidth_gbs(Scene &s, size_t bytes, int iters);
 }    // namespace crb

@@ -29,7 +29,7 @@ namespace crb
         // persistent kernels: each warp is a pool of 32 traversal lanes refilled from `cursor` (bvh8.cuh)
         template<bool COUNT>
         __global__ void __launch_bounds__(256, 4) k_intersect_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits,
-                                                                 uint32_t *cursor, unsigned long long *ctr)
+                                                                 uint32_t *cursor, unsigned long long *ctr, int postpone)
         {
             TravCounters tc;
             auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
@@ -45,7 +45,7 @@ namespace crb
                 if (h.prim != INVALID_PRIM) resolve_flat(sc, h.prim, out.prim, out.model, out.inst);
                 hits[item] = out;
             };
-            trace_persistent<false, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, source, sink, &tc);
+            trace_persistent<false, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, postpone, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ctr + 0, tc.nodes);
@@ -55,7 +55,7 @@ namespace crb
 
         template<bool COUNT>
         __global__ void __launch_bounds__(256, 4) k_occluded_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, uint8_t *__restrict__ occ,
-                                                                uint32_t *cursor, unsigned long long *ctr)
+                                                                uint32_t *cursor, unsigned long long *ctr, int postpone)
         {
             TravCounters tc;
             auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
@@ -64,9 +64,9 @@ namespace crb
                 o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z), tmin = a.w, tmax = b.w;
             };
             auto sink = [&](bool valid, uint32_t item, const Hit &h) {
-                if (!COUNT && valid) occ[item] = h.prim != INVALID_PRIM ? 1 : 0;
+                if (occ && valid) occ[item] = h.prim != INVALID_PRIM ? 1 : 0;
             };
-            trace_persistent<true, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, source, sink, &tc);
+            trace_persistent<true, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, postpone, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ctr + 0, tc.nodes);
@@ -147,14 +147,15 @@ namespace crb
                 const unsigned g = unsigned(s.n_sms) * 4, blk = B;
 #endif
                 const uint32_t cnt32 = uint32_t(cnt);
+                static const int postpone = getenv("CRB_POSTPONE") ? atoi(getenv("CRB_POSTPONE")) : 1;    // tuning knob
                 dev_zero(d_cursor.p, 4, s.stream);
                 timer.start();
                 switch (mode)
                 {
-                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), d_cursor.p, d_ctr.p); break;
-                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<uint8_t *>(op), d_cursor.p, d_ctr.p); break;
-                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, blk, s.stream, sc, rp, cnt32, (crb_hit *) nullptr, d_cursor.p, d_ctr.p); break;
-                default: CRB_LAUNCH((k_occluded_batch<true>), g, blk, s.stream, sc, rp, cnt32, (uint8_t *) nullptr, d_cursor.p, d_ctr.p); break;
+                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), d_cursor.p, d_ctr.p, postpone); break;
+                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<uint8_t *>(op), d_cursor.p, d_ctr.p, postpone); break;
+                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, blk, s.stream, sc, rp, cnt32, (crb_hit *) nullptr, d_cursor.p, d_ctr.p, postpone); break;
+                default: CRB_LAUNCH((k_occluded_batch<true>), g, blk, s.stream, sc, rp, cnt32, (uint8_t *) nullptr, d_cursor.p, d_ctr.p, postpone); break;
                 }
                 ms += timer.stop();
                 if (!on_device && mode < 2) dev_download(static_cast<char *>(out) + off * out_elem, d_out.p, cnt * out_elem, s.stream);
@@ -178,5 +179,54 @@ namespace crb
         run_batch(s, rays, nullptr, n, on_device, any_hit ? 3 : 2, c);
         if (nodes) *nodes = c[0];
         if (tris) *tris = c[1];
+    }
+}    // namespace crb
+
+// ---------------------------------------------------------------------------------------------------
+// Memory-system micro-benchmark used for the roofline context: read `bytes` of device
+// memory `iters` times with 16-byte loads. A working set below the L2 size measures L2 bandwidth, a large
+// one measures HBM read bandwidth.
+namespace crb
+{
+    namespace
+    {
+        __global__ void __launch_bounds__(256) k_read_bw(const uint4 *__restrict__ p, size_t n16, int iters, unsigned *sink)
+        {
+            unsigned     acc    = 0;
+            const size_t stride = size_t(gridDim.x) * blockDim.x;
+            for (int it = 0; it < iters; it++)
+                for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride)
+                {
+                    const uint4 v = p[i];
+                    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+                }
+            if (acc == 0x12345678u) *sink = acc;    // never true in practice; keeps the loads alive
+        }
+    }    // namespace
+
+    double read_bandwidth_gbs(Scene &s, size_t bytes, int iters)
+    {
+#ifdef CRB_EMU
+        (void) s, (void) bytes, (void) iters;
+        return 0.0;
+#else
+        DBuf<uint4>    buf;
+        DBuf<unsigned> sink;
+        const size_t   n16 = bytes / 16;
+        buf.alloc(n16), sink.alloc(1);
+        dev_fill_byte(buf.p, 1, n16 * 16, s.stream);
+        CRB_LAUNCH(k_read_bw, unsigned(s.n_sms) * 8, 256, s.stream, buf.p, n16, 1, sink.p);    // warm
+        cudaEvent_t e0, e1;
+        CRB_CUDA_CHECK(cudaEventCreate(&e0));
+        CRB_CUDA_CHECK(cudaEventCreate(&e1));
+        CRB_CUDA_CHECK(cudaEventRecord(e0, s.stream));
+        CRB_LAUNCH(k_read_bw, unsigned(s.n_sms) * 8, 256, s.stream, buf.p, n16, iters, sink.p);
+        CRB_CUDA_CHECK(cudaEventRecord(e1, s.stream));
+        CRB_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        return double(n16) * 16.0 * iters / (double(ms) * 1e-3) / 1e9;
+#endif
     }
 }    // namespace crb

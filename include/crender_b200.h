@@ -165,6 +165,9 @@ int crb_occluded_batch(crb_scene *, const crb_ray *rays, uint8_t *occluded, uint
 /* instrumented traversal: mean node visits / triangle tests per ray for the roofline */
 int crb_trace_counters(crb_scene *, const crb_ray *rays, uint64_t n, int on_device, int any_hit, uint64_t *node_visits,
                        uint64_t *tri_tests);
+/* memory-system micro-benchmark for the roofline context: reads `bytes` of device memory `iters` times
+ * with 16-byte loads and returns GB/s (working set < L2 size: L2 bandwidth; large: HBM read bandwidth) */
+int crb_microbench_read(crb_scene *, uint64_t bytes, int iters, double *gb_per_s);
 /* device time of the last crb_intersect_batch / crb_occluded_batch kernel, ms */
 int crb_last_query_ms(crb_scene *, double *ms);
 
