@@ -3,7 +3,7 @@
 // Replaces rtcCommitGeometry/rtcAttachGeometry/rtcCommitScene (src/objects/model.cpp:92-94), which in
 // the reference is Embree's CPU binned-SAH builder. Pipeline, all on the device:
 //   K1  k_prim_bounds  per-triangle AABBs + centroid bounds (warp-reduced ordered-int atomics)
-//       k_morton       63-bit Morton keys of the centroids; radix sort of (key, prim) pairs
+//       k_morton       63-bit Morton keys of the centroids; hand-written stable LSD radix sort of (key, prim) pairs (radix_sort.cuh)
 //   K2  k_hierarchy    LBVH topology from sorted keys (Karras 2012, one thread per inner node)
 //       k_refit        bottom-up AABBs + subtree SAH cost with per-node arrival counters
 //   K3  k_treelet      SAH treelet restructuring (Karras & Aila 2013, 7-leaf treelets, exact DP)
@@ -18,9 +18,7 @@
 #include <chrono>
 #include <vector>
 
-#ifndef CRB_EMU
-#include <cub/device/device_radix_sort.cuh>
-#endif
+#include "radix_sort.cuh"
 
 namespace crb
 {
@@ -97,6 +95,12 @@ namespace crb
                                      qz = (unsigned long long) fminf(fmaxf(fz, 0.f), k - 1.f);
             keys[i] = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
             vals[i] = i;
+        }
+
+        __global__ void k_check_sorted(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t *bad)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i + 1 < n && keys[i] > keys[i + 1]) atomicAdd(bad, 1u);
         }
 
         // common-prefix length of sorted keys i and j, ties broken by position (Karras 2012 §4)
@@ -528,6 +532,9 @@ namespace crb
         sz(ni, 4), sz(ni, 4), sz(ni, 4), sz(n, 4), sz(ni, 4), sz(ni, 16), sz(ni, 16), sz(ni, 4), sz(ni, 28), sz(ni, 8);    // tree + collapse DP tables
         sz(max_nodes, 8), sz(max_nodes, 8);   // collapse queues
         sz(8, 4);                             // counters + sah
+#ifndef CRB_EMU
+        sz(radix_sort_hist_entries(n), 4);    // radix sort histograms
+#endif
         DBuf<char> scratch;
         scratch.alloc(bytes + 4096);
         char   *p    = scratch.p;
@@ -544,6 +551,9 @@ namespace crb
         t.dpk        = carve<unsigned char>(p, ni * 8);
         uint2    *q0 = carve<uint2>(p, max_nodes), *q1 = carve<uint2>(p, max_nodes);
         uint32_t *counters = carve<uint32_t>(p, 8);
+#ifndef CRB_EMU
+        uint32_t *rs_hist = carve<uint32_t>(p, radix_sort_hist_entries(n));
+#endif
 
         const int      B  = 256;
         const unsigned gn = (n + B - 1) / B;
@@ -570,12 +580,16 @@ namespace crb
         }
 #else
         {
-            size_t tmp_bytes = 0;
-            CRB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys0, keys1, vals0, vals1, int(n), 0, 63, stream));
-            DBuf<char> tmp;
-            tmp.alloc(tmp_bytes);
-            CRB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys0, keys1, vals0, vals1, int(n), 0, 63, stream));
-            stream_sync(stream);    // tmp is freed at scope exit
+            // hand-written stable LSD radix sort (radix_sort.cuh): 8 passes of 8 bits over the 63-bit keys
+            const int where = radix_sort_pairs(keys0, vals0, keys1, vals1, n, 63, rs_hist, stream);
+            keys            = where ? keys1 : keys0;
+            vals            = where ? vals1 : vals0;
+            // loud failure instead of a silently broken tree
+            dev_zero(counters + 6, 4, stream);
+            CRB_LAUNCH(k_check_sorted, gn, B, stream, keys, n, counters + 6);
+            uint32_t bad = 0;
+            dev_download(&bad, counters + 6, 4, stream);
+            if (bad) throw Error(ERR_GENERIC, "internal: Morton key sort produced an unsorted sequence");
         }
 #endif
 

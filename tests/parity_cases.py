@@ -184,3 +184,85 @@ def check_first_hit_via_batch(oracle, lib_path, desc, w, h):
     ro = oracle.renderer(w, h, 1, o, seed=3)
     ph = ro.primary_hits(0)
     return ph, g
+
+
+def check_update_semantics(oracle, lib_path):
+    """renderer::update = pause -> mutate -> restart from sample 0 (renderer.cpp:185-192); material edits
+    need no rebuild (ui.h:924-929), instance edits do (ui.h:1183-1192); set_resolution / set_max_bounces
+    (renderer.cpp:194-213); un-rendered pixels keep cr::image's FLT_MAX fill (image.h:30-38)."""
+    desc = scenes.textured_scene()
+    o, g = build_pair(oracle, lib_path, desc)
+    w, h = 64, 48
+    rg = api.renderer(w, h, 5, g, seed=2)
+    rg.render(3)
+    before = rg.raw_sum().copy()
+
+    # 1. material edit through update(): restarts from sample 0, no re-commit
+    new_mats = [material(api.METAL, colour=(0.2, 0.9, 0.3, 1.0), reflectiveness=0.7), material(api.SMOOTH, colour=(0.9, 0.1, 0.1, 1.0)), material(api.GLASS, ior=1.3)]
+    nodes_before = g.build_info.n_nodes
+    rg.update(lambda: g.set_materials(2, new_mats))
+    assert rg.current_stats().passes == 0
+    rg.render(3)
+    after = rg.raw_sum().copy()
+    assert not np.array_equal(before, after)
+    o.set_materials(2, new_mats)
+    ro = oracle.renderer(w, h, 5, o, seed=2)
+    ro.render(3)
+    assert common.relrmse(after[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE
+    assert g.build_info.n_nodes == nodes_before
+
+    # 2. instance edit: needs a commit (the rtcCommitScene point); render before commit is an error
+    inst = np.stack([scenes.translation(-0.8, 0.0, 1.0), scenes.compose(scenes.translation(0.9, 0.1, 1.6), scenes.rotation_y(-20.0))]).astype(np.float32)
+    g.set_instances(2, inst)
+    try:
+        rg.start()
+        rg.render(1)
+        raise AssertionError("render after an instance edit without commit must fail")
+    except api.CrbError as e:
+        assert e.code == 33
+    g.commit()
+    rg.start()
+    rg.render(3)
+    o.set_instances(2, inst)
+    o.commit()
+    ro = oracle.renderer(w, h, 5, o, seed=2)
+    ro.render(3)
+    assert common.relrmse(rg.raw_sum()[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE
+
+    # 3. set_max_bounces / set_resolution
+    rg.set_max_bounces(2)
+    rg.start()
+    rg.render(2)
+    ro = oracle.renderer(w, h, 2, o, seed=2)
+    ro.render(2)
+    assert common.relrmse(rg.raw_sum()[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE
+    rg.set_resolution(40, 30)
+    assert rg.current_resolution() == (40, 30)
+    rg.render(2)
+    ro = oracle.renderer(40, 30, 2, o, seed=2)
+    ro.render(2)
+    assert rg.raw_sum().shape == (30, 40, 4)
+    assert common.relrmse(rg.raw_sum()[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE
+
+    # 4. FLT_MAX fill of pixels never rendered, sun toggle, camera change picked up through update()
+    rg.start()
+    rg.set_rows(0, 10)
+    rg.render(1)
+    disp = rg.current_progress()
+    flt_max = np.float32(3.4028234663852886e38)
+    assert np.all(disp[:20] == flt_max) and np.all(disp[20:, :, 3] == 1.0)  # sample rows 0..9 land in flipped rows 20..29
+    rg.set_rows(0, 30)
+    cam2 = api.camera(position=(0.3, 1.0, -3.0), fov=60.0, rotation=(-3.0, 10.0, 0.0))
+
+    def mutate():
+        g.set_sun_enabled(False)
+        g.set_camera(cam2)
+
+    rg.update(mutate)
+    rg.render(2)
+    o.set_sun_enabled(False)
+    o.set_camera(cam2)
+    ro = oracle.renderer(40, 30, 2, o, seed=2)
+    ro.render(2)
+    assert common.relrmse(rg.raw_sum()[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE
+    assert rg.current_stats().total_queries == rg.current_stats().closest_queries  # sun off: no shadow rays

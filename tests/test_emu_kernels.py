@@ -33,3 +33,7 @@ def test_edge_cases(emu_lib):
 def test_larger_build(oracle, emu_lib):
     # 80k triangles: exercises deeper trees, many collapse levels and duplicate Morton keys
     pc.check_hits(oracle, emu_lib, scenes.mesh_scene(200, 200, with_ground=False), n_rays=4000)
+
+
+def test_update_semantics(oracle, emu_lib):
+    pc.check_update_semantics(oracle, emu_lib)

@@ -167,3 +167,7 @@ def test_cpp_host_mirror_cli_matches_python_api(product_lib, tmp_path):
     ref = r.current_progress()
     # same library, same geometry (the CLI indexes its quads, the Python scene is a soup): identical floats
     assert common.relrmse(img[..., :3], ref[..., :3]) < 1e-6
+
+
+def test_update_semantics(oracle, product_lib):
+    pc.check_update_semantics(oracle, product_lib)
