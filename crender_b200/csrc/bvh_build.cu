@@ -205,9 +205,10 @@ namespace crb
         //          = A(n) c_node + D(n,8)                  otherwise (n becomes a wide node)
         //   C(n,i) = min(D(n,i), C(n,i-1)),  D(n,j) = min_{0<k<j} C(left,k) + C(right,j-k)
         // c_node : c_prim follows the measured instruction cost of a node test vs a triangle test (~3:1).
-        constexpr float DP_CNODE = 1.0f, DP_CPRIM = 0.35f;
+        constexpr float DP_CNODE = 1.0f;
 
-        __global__ void k_collapse_dp(int n, BinTree t, const float4 *__restrict__ plo, const float4 *__restrict__ phi, const uint32_t *__restrict__ vals)
+        __global__ void k_collapse_dp(int n, BinTree t, const float4 *__restrict__ plo, const float4 *__restrict__ phi, const uint32_t *__restrict__ vals,
+                                      float DP_CPRIM)
         {
             const int i = blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= n) return;
@@ -628,7 +629,7 @@ namespace crb
         if (c.use_dp)
         {
             dev_zero(t.flags, ni * sizeof(int), stream);
-            CRB_LAUNCH(k_collapse_dp, gn, B, stream, int(n), t, plo, phi, vals);
+            CRB_LAUNCH(k_collapse_dp, gn, B, stream, int(n), t, plo, phi, vals, opt.cost_prim);
         }
         uint32_t n_in  = 1;
         uint32_t depth = 0;

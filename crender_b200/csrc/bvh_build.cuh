@@ -20,6 +20,7 @@ namespace crb
     {
         int  treelet_passes = 1;       // SAH treelet restructuring sweeps (a second sweep buys <0.5 % rays/s for +11 ms at 1M triangles)
         bool optimal_collapse = true;  // SAH-optimal (dynamic programming) binary -> 8-wide collapse; false = greedy by area
+        float cost_prim = 0.8f;        // collapse DP: cost of a triangle test relative to an 8-wide node test (swept: profiles/r1c_sweeps.md)
     };
 
     // wverts: device pointer, 9 floats per triangle (world space), n triangles.

@@ -309,6 +309,7 @@ namespace crb
         BuildOptions opt;
         if (const char *e = getenv("CRB_TREELET_PASSES")) opt.treelet_passes = atoi(e);    // build-quality experiments
         if (const char *e = getenv("CRB_OPTIMAL_COLLAPSE")) opt.optimal_collapse = atoi(e) != 0;
+        if (const char *e = getenv("CRB_COST_PRIM")) opt.cost_prim = float(atof(e));
         build_bvh8(d_wverts.p, n_flat, stream, opt, d_nodes, d_tris, build);
         d_wverts.release();
         committed = true;
