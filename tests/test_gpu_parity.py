@@ -171,3 +171,41 @@ def test_cpp_host_mirror_cli_matches_python_api(product_lib, tmp_path):
 
 def test_update_semantics(oracle, product_lib):
     pc.check_update_semantics(oracle, product_lib)
+
+
+def test_against_golden_fixtures(product_lib):
+    """The CUDA path against the committed fixtures (no oracle at run time for this test)."""
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+
+    gold = np.load(os.path.join(here, "golden", "golden_v1.npz"))
+    for name in ("cornell", "mesh", "textured", "terrain"):
+        desc = common.small_scenes()[name]
+        g = api.scene(lib_path=product_lib)
+        scenes.load(desc, g)
+        g.commit()
+        rays = common.mixed_rays(desc, make_golden.N_RAYS, seed=101)
+        h = g.cast_rays(rays)
+        identity_only = all(m.instances is None for m in desc.meshes)
+        same = (h["prim"] == gold[f"{name}/hit_prim"]) & (h["model"] == gold[f"{name}/hit_model"]) & (h["inst"] == gold[f"{name}/hit_inst"])
+        if identity_only:
+            assert same.all()
+            np.testing.assert_array_equal(h["t"], gold[f"{name}/hit_t"])
+            np.testing.assert_array_equal(h["u"], gold[f"{name}/hit_u"])
+        else:
+            assert same.mean() >= pc.PRIM_AGREE
+        np.testing.assert_array_equal(g.occluded(rays).astype(bool)[same], gold[f"{name}/occluded"].astype(bool)[same])
+        w, hh, spp, bounces, seed = make_golden.IMAGES[name]
+        r = api.renderer(w, hh, bounces, g, seed=seed)
+        r.render(spp)
+        assert common.relrmse(r.raw_sum()[..., :3], gold[f"{name}/raw"][..., :3]) <= pc.IMG_RELRMSE
+        assert common.relrmse(r.current_progress()[..., :3], gold[f"{name}/progress"][..., :3]) <= pc.IMG_RELRMSE
+        for aov, img in (("albedo", r.current_albedos()), ("normal", r.current_normals()), ("depth", r.current_depths())):
+            ok = np.all(np.abs(img - gold[f"{name}/{aov}"]) <= 1e-5 * np.maximum(1.0, np.abs(gold[f"{name}/{aov}"])), axis=-1)
+            assert ok.mean() >= 0.999, (name, aov, ok.mean())
+        st = r.current_stats()
+        assert int(st.passes) == int(gold[f"{name}/stats"][3]) and int(st.pixel_samples) == int(gold[f"{name}/stats"][2])
