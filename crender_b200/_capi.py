@@ -104,6 +104,7 @@ SIGNATURES = {
     "crb_render_sync": (C.c_int, [_P]),
     "crb_render_read": (C.c_int, [_P, C.c_int, _P]),
     "crb_render_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "crb_render_restore": (C.c_int, [_P, _P, C.c_uint32]),
     "crb_render_accum_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "crb_render_set_pass_count": (C.c_int, [_P, C.c_uint32]),
     "crb_render_resolve": (C.c_int, [_P]),

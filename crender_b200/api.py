@@ -342,6 +342,17 @@ class renderer:
         _capi.check(self._lib, self._lib.crb_render_stats(self._h, C.byref(st)))
         return st
 
+    # ---- checkpoint / resume
+    def checkpoint(self) -> np.ndarray:
+        """The accumulation buffer (RGBA, A = pass count): a complete checkpoint of the progressive render."""
+        return self.raw_sum()
+
+    def restore(self, raw_sum: np.ndarray):
+        a = np.ascontiguousarray(raw_sum, dtype=np.float32)
+        passes = int(a[..., 3].max()) if a.size else 0
+        _capi.check(self._lib, self._lib.crb_render_restore(self._h, _ptr(a), passes))
+        self._next_sample = passes
+
     # ---- multi-GPU plumbing
     def accum_ptr(self):
         p, n = C.c_void_p(), C.c_uint64(0)

@@ -310,6 +310,14 @@ int crb_render_stats(crb_render *r, crb_stats *out)
         r->r.stats(*out);
     });
 }
+int crb_render_restore(crb_render *r, const float *raw, uint32_t passes)
+{
+    return guarded([&] {
+        need(r, "render");
+        need(raw, "raw_sum_rgba_host");
+        r->r.restore(raw, passes);
+    });
+}
 int crb_render_accum_ptr(crb_render *r, void **p, uint64_t *n)
 {
     return guarded([&] {

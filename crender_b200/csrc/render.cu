@@ -869,6 +869,16 @@ namespace crb
         dev_download(dst, src, size_t(w) * h * 16, stream());
     }
 
+    void Render::restore(const float *raw_sum_rgba, uint32_t passes_)
+    {
+        sync();
+        dev_upload(accum.p, raw_sum_rgba, size_t(w) * h * 16, stream());
+        stream_sync(stream());
+        passes = passes_;
+        resolve();
+        sync();
+    }
+
     void Render::stats(crb_stats &out)
     {
         sync();

@@ -93,6 +93,7 @@ namespace crb
         void sync();
         void resolve();
         void read(int kind, float *dst);
+        void restore(const float *raw_sum_rgba, uint32_t passes_);
         void stats(crb_stats &out);
 
     private:

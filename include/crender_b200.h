@@ -194,6 +194,10 @@ enum { CRB_RAW_SUM = 0, CRB_PROGRESS = 1, CRB_ALBEDO = 2, CRB_NORMAL = 3, CRB_DE
  * flipped exactly as the reference stores them. CRB_RAW_SUM = _raw_buffer as RGBA with A = passes. */
 int crb_render_read(crb_render *, int kind, float *dst_host);
 int crb_render_stats(crb_render *, crb_stats *out); /* renderer::current_stats, renderer.cpp:396-404 */
+/* checkpoint / resume (the reference restarts from 0 spp on every start(), renderer.cpp:154-170): a
+ * CRB_RAW_SUM read is a complete checkpoint; restore uploads it (w*h*4 floats) with its pass count, after
+ * which crb_render_samples(first_sample = passes, ...) continues the same progressive render bit for bit */
+int crb_render_restore(crb_render *, const float *raw_sum_rgba_host, uint32_t passes);
 /* multi-GPU plumbing: the float4 accumulation buffer (device pointer, w*h*4 floats) so that the
  * caller's collective (torch.distributed/NCCL) can reduce it in place, then set the merged pass count
  * and re-resolve the display buffer. */

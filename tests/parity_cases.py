@@ -266,3 +266,25 @@ def check_update_semantics(oracle, lib_path):
     ro.render(2)
     assert common.relrmse(rg.raw_sum()[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE
     assert rg.current_stats().total_queries == rg.current_stats().closest_queries  # sun off: no shadow rays
+
+
+def check_checkpoint_resume(lib_path):
+    """accumulator checkpoint/resume. Rendering 8 passes in one go and rendering 5,
+    checkpointing, restoring into a NEW renderer and rendering 3 more must agree bit for bit."""
+    desc = scenes.mesh_scene(40, 20)
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    r = api.renderer(72, 40, 5, g, seed=6)
+    r.render(8)
+    whole_raw, whole_disp = r.raw_sum().copy(), r.current_progress().copy()
+    r2 = api.renderer(72, 40, 5, g, seed=6)
+    r2.render(5)
+    ckpt = r2.checkpoint().copy()
+    del r2
+    r3 = api.renderer(72, 40, 5, g, seed=6)
+    r3.restore(ckpt)
+    assert r3.current_stats().passes == 5
+    r3.render(3)  # continues at first_sample = 5
+    np.testing.assert_array_equal(r3.raw_sum(), whole_raw)
+    np.testing.assert_array_equal(r3.current_progress(), whole_disp)

@@ -37,3 +37,7 @@ def test_larger_build(oracle, emu_lib):
 
 def test_update_semantics(oracle, emu_lib):
     pc.check_update_semantics(oracle, emu_lib)
+
+
+def test_checkpoint_resume(emu_lib):
+    pc.check_checkpoint_resume(emu_lib)

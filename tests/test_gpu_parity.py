@@ -209,3 +209,7 @@ def test_against_golden_fixtures(product_lib):
             assert ok.mean() >= 0.999, (name, aov, ok.mean())
         st = r.current_stats()
         assert int(st.passes) == int(gold[f"{name}/stats"][3]) and int(st.pixel_samples) == int(gold[f"{name}/stats"][2])
+
+
+def test_checkpoint_resume(product_lib):
+    pc.check_checkpoint_resume(product_lib)
