@@ -726,7 +726,17 @@ namespace crb
         collect_time();
         const uint32_t nrows = row1 - row0;
         const uint32_t npix  = w * nrows;
-        uint32_t       spp_batch = uint32_t(std::max<size_t>(1, target_paths / npix));
+        static const size_t tp_env = getenv("CRB_TARGET_PATHS") ? size_t(atoll(getenv("CRB_TARGET_PATHS"))) : 0;    // tuning knob
+        size_t         tpaths    = tp_env ? tp_env : target_paths;
+#ifndef CRB_EMU
+        {
+            // never plan for more than a quarter of the free device memory (152 B of state per path)
+            size_t free_b = 0, total_b = 0;
+            if (capacity == 0 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) mem_path_cap = std::max<size_t>(size_t(1) << 20, free_b / 4 / 152);
+            if (mem_path_cap) tpaths = std::min(tpaths, mem_path_cap);
+        }
+#endif
+        uint32_t       spp_batch = uint32_t(std::max<size_t>(1, tpaths / npix));
         spp_batch                = std::min(spp_batch, n);
         ensure_paths(size_t(npix) * spp_batch);
 

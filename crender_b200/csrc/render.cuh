@@ -63,7 +63,10 @@ namespace crb
         double   device_ms = 0;
         uint64_t launches  = 0;
         uint64_t pixel_samples = 0;
-        size_t   target_paths = size_t(1) << 23;    // paths in flight per batch
+        // paths in flight per batch: bigger batches amortise kernel tails and keep the late, thin bounces
+        // wide enough for 148 SMs (swept in profiles/r1c_sweeps.md §10); 152 B of path state each
+        size_t   target_paths = size_t(1) << 25;
+        size_t   mem_path_cap = 0;
         double   kernel_ms[8]    = {};
         uint64_t kernel_count[8] = {};
 #ifndef CRB_EMU
