@@ -54,6 +54,20 @@ class BuildInfo(C.Structure):
     ]
 
 
+class PostSettings(C.Structure):
+    # cr::post_processor::*_settings, src/render/post/post_processor.h:19-39
+    _fields_ = [
+        ("use_bloom", C.c_int32),
+        ("bloom_threshold", C.c_float),
+        ("bloom_strength", C.c_float),
+        ("use_gray_scale", C.c_int32),
+        ("use_tonemapping", C.c_int32),
+        ("tonemapping_type", C.c_int32),
+        ("tonemapping_exposure", C.c_float),
+        ("gamma_correction", C.c_float),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("total_queries", C.c_uint64),
@@ -105,6 +119,8 @@ SIGNATURES = {
     "crb_render_read": (C.c_int, [_P, C.c_int, _P]),
     "crb_render_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "crb_render_restore": (C.c_int, [_P, _P, C.c_uint32]),
+    "crb_post_process": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.POINTER(PostSettings), _P]),
+    "crb_render_post_process": (C.c_int, [_P, C.POINTER(PostSettings), _P]),
     "crb_render_accum_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "crb_render_set_pass_count": (C.c_int, [_P, C.c_uint32]),
     "crb_render_resolve": (C.c_int, [_P]),

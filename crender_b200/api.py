@@ -89,6 +89,13 @@ def _c_material(m: material) -> _capi.Material:
     return cm
 
 
+def post_settings(use_bloom=False, bloom_threshold=0.7, bloom_strength=1.0, use_gray_scale=False, use_tonemapping=False, tonemapping_type=0,
+                  tonemapping_exposure=1.0, gamma_correction=2.2) -> _capi.PostSettings:
+    """cr::post_processor settings with the reference's defaults (post_processor.h:19-39)."""
+    return _capi.PostSettings(int(use_bloom), bloom_threshold, bloom_strength, int(use_gray_scale), int(use_tonemapping), tonemapping_type,
+                              tonemapping_exposure, gamma_correction)
+
+
 class scene:
     """cr::scene. Geometry changes take effect at commit() (the rtcCommitScene point)."""
 
@@ -226,6 +233,13 @@ class scene:
         _capi.check(self._lib, self._lib.crb_microbench_read(self._h, nbytes, iters, C.byref(g)))
         return g.value
 
+    def post_process(self, rgba, settings: _capi.PostSettings) -> np.ndarray:
+        """cr::post_processor::process on a host RGBA image, run as CUDA kernels."""
+        a = _f32(rgba)
+        out = np.empty_like(a)
+        _capi.check(self._lib, self._lib.crb_post_process(self._h, _ptr(a), a.shape[1], a.shape[0], C.byref(settings), _ptr(out)))
+        return out
+
     def last_query_ms(self) -> float:
         ms = C.c_double(0)
         _capi.check(self._lib, self._lib.crb_last_query_ms(self._h, C.byref(ms)))
@@ -341,6 +355,13 @@ class renderer:
         st = _capi.Stats()
         _capi.check(self._lib, self._lib.crb_render_stats(self._h, C.byref(st)))
         return st
+
+    def post_process(self, settings: _capi.PostSettings) -> np.ndarray:
+        """The post chain applied to the device-resident display buffer (export path, ui.h:567-631)."""
+        w, h = self._res
+        out = np.empty((h, w, 4), dtype=np.float32)
+        _capi.check(self._lib, self._lib.crb_render_post_process(self._h, C.byref(settings), _ptr(out)))
+        return out
 
     # ---- checkpoint / resume
     def checkpoint(self) -> np.ndarray:

@@ -230,6 +230,32 @@ int crb_scene_stream(crb_scene *s, void **stream)
     });
 }
 
+int crb_post_process(crb_scene *s, const float *rgba, uint32_t w, uint32_t h, const crb_post_settings *ps, float *out)
+{
+    return guarded([&] {
+        need(s, "scene");
+        need(rgba, "rgba_host");
+        need(ps, "settings");
+        need(out, "out_host");
+        if (!w || !h) throw crb::Error(crb::ERR_INVALID_ARG, "post_process: empty image");
+        crb::DBuf<float4> src;
+        src.alloc(size_t(w) * h);
+        crb::dev_upload(src.p, rgba, size_t(w) * h * 16, s->s.stream);
+        crb::post_process(s->s, src.p, w, h, *ps, out);
+        crb::stream_sync(s->s.stream);
+    });
+}
+int crb_render_post_process(crb_render *r, const crb_post_settings *ps, float *out)
+{
+    return guarded([&] {
+        need(r, "render");
+        need(ps, "settings");
+        need(out, "out_host");
+        r->r.sync();
+        crb::post_process(*r->r.scene, r->r.display.p, r->r.w, r->r.h, *ps, out);
+    });
+}
+
 // ------------------------------------------------------------------ renderer
 int crb_render_create(crb_scene *s, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags, crb_render **out)
 {

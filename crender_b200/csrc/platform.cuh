@@ -195,6 +195,7 @@ inline T __shfl_down_sync(unsigned, T v, int)
 inline void __syncwarp(unsigned = 0xffffffffu) {}
 inline void __syncthreads() {}    // emulated launches use one thread per block
 #define __shared__ static
+#define __constant__
 inline void __threadfence() {}
 template<typename T>
 inline T __ldg(const T *p)

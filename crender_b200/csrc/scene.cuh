@@ -147,4 +147,6 @@ namespace crb
     void occluded_batch(Scene &s, const crb_ray *rays, uint8_t *occ, uint64_t n, bool on_device);
     void trace_counters(Scene &s, const crb_ray *rays, uint64_t n, bool on_device, bool any_hit, uint64_t *nodes, uint64_t *tris);
     double read_bandwidth_gbs(Scene &s, size_t bytes, int iters);
+    // export-time post chain (post.cu)
+    void post_process(Scene &sc, const float4 *d_src, uint32_t w, uint32_t h, const crb_post_settings &s, float *out_host);
 }    // namespace crb

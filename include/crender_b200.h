@@ -126,6 +126,19 @@ typedef struct crb_stats
 } crb_stats;
 enum { CRB_K_RAYGEN = 0, CRB_K_TRACE = 1, CRB_K_SHADE = 2, CRB_K_SHADOW = 3, CRB_K_ADVANCE = 4, CRB_K_ACCUMULATE = 5 };
 
+/* cr::post_processor::{bloom,gray_scale,tonemapping}_settings, src/render/post/post_processor.h:19-39 */
+typedef struct crb_post_settings
+{
+    int32_t use_bloom;            /* false */
+    float   bloom_threshold;      /* 0.7 */
+    float   bloom_strength;       /* 1.0 */
+    int32_t use_gray_scale;       /* false */
+    int32_t use_tonemapping;      /* false */
+    int32_t tonemapping_type;     /* 0 linear, 1 reinhard, 2 jim-richard, 3 uncharted */
+    float   tonemapping_exposure; /* 1.0 */
+    float   gamma_correction;     /* 2.2 */
+} crb_post_settings;
+
 typedef struct crb_scene  crb_scene;
 typedef struct crb_render crb_render;
 
@@ -198,6 +211,11 @@ int crb_render_stats(crb_render *, crb_stats *out); /* renderer::current_stats, 
  * CRB_RAW_SUM read is a complete checkpoint; restore uploads it (w*h*4 floats) with its pass count, after
  * which crb_render_samples(first_sample = passes, ...) continues the same progressive render bit for bit */
 int crb_render_restore(crb_render *, const float *raw_sum_rgba_host, uint32_t passes);
+/* cr::post_processor::process (src/render/post/post_processor.cpp:110-296 + post_process.comp, blur.comp)
+ * as CUDA kernels, no GL context: bloom (threshold, 10 blur passes), gray scale, 4 tonemappers. The first
+ * form takes any host RGBA image, the second the renderer's device-resident display buffer. */
+int crb_post_process(crb_scene *, const float *rgba_host, uint32_t w, uint32_t h, const crb_post_settings *, float *out_host);
+int crb_render_post_process(crb_render *, const crb_post_settings *, float *out_host);
 /* multi-GPU plumbing: the float4 accumulation buffer (device pointer, w*h*4 floats) so that the
  * caller's collective (torch.distributed/NCCL) can reduce it in place, then set the merged pass count
  * and re-resolve the display buffer. */

@@ -288,3 +288,32 @@ def check_checkpoint_resume(lib_path):
     r3.render(3)  # continues at first_sample = 5
     np.testing.assert_array_equal(r3.raw_sum(), whole_raw)
     np.testing.assert_array_equal(r3.current_progress(), whole_disp)
+
+
+def check_post_chain(lib_path):
+    """the export-time post chain as CUDA kernels against the numpy restatement of the
+    reference's GLSL (tests/post_oracle.py). Tolerance 2e-5 relative: powf / GLSL pow differ by ulps."""
+    import post_oracle
+
+    g = api.scene(lib_path=lib_path)
+    g.commit()
+    rs = np.random.RandomState(3)
+    for (w, h) in ((32, 32), (40, 27), (24, 48)):  # square, not multiples of 8, taller than wide
+        img = rs.uniform(0.0, 1.4, (h, w, 4)).astype(np.float32)
+        img[..., 3] = 1.0
+        cases = [dict(), dict(use_gray_scale=True), dict(use_bloom=True, bloom_threshold=0.8, bloom_strength=0.6)]
+        cases += [dict(use_tonemapping=True, tonemapping_type=t, tonemapping_exposure=1.3, gamma_correction=2.2) for t in range(4)]
+        cases += [dict(use_bloom=True, use_gray_scale=True, use_tonemapping=True, tonemapping_type=1)]
+        for kw in cases:
+            got = g.post_process(img, api.post_settings(**kw))
+            ref = post_oracle.process(img, **kw)
+            np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6, err_msg=str((w, h, kw)))
+    # the renderer-side entry point works on the device-resident display buffer
+    desc = scenes.cornell()
+    gs = api.scene(lib_path=lib_path)
+    scenes.load(desc, gs)
+    gs.commit()
+    r = api.renderer(48, 40, 4, gs, seed=1)
+    r.render(2)
+    kw = dict(use_tonemapping=True, tonemapping_type=3, use_bloom=True)
+    np.testing.assert_allclose(r.post_process(api.post_settings(**kw)), post_oracle.process(r.current_progress(), **kw), rtol=2e-5, atol=2e-6)

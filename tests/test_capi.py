@@ -62,3 +62,22 @@ def test_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle_binding" not in text and "liboracle" not in text and "oracle/" not in text.replace("oracle/_", ""), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary must be bindable from C (cgo/JNI/ctypes-style FFI): the header compiles as C99 and a C
+    program that references every entry point links against the library."""
+    names = declared_functions()
+    src = tmp_path / "use.c"
+    body = "\n".join(f"    p[{i}] = (fn) {n};" for i, n in enumerate(names))
+    src.write_text(f'#include "crender_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {{\n    fn p[{len(names)}];\n{body}\n'
+                   f'    printf("%d\\n", p[0] != 0);\n    crb_scene *s = 0;\n    int rc = crb_scene_create(&s);\n    printf("%d %s\\n", rc, crb_last_error());\n    return 0;\n}}\n')
+    exe = tmp_path / "use"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+                    f"-L{os.path.join(ROOT, 'crender_b200')}", "-lcrender_b200", f"-Wl,-rpath,{os.path.join(ROOT, 'crender_b200')}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0
+    import torch
+
+    if not torch.cuda.is_available():
+        assert out.stdout.splitlines()[-1].startswith("10 ")  # CRB_ERR_NO_DEVICE, loudly

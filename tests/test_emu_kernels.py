@@ -41,3 +41,7 @@ def test_update_semantics(oracle, emu_lib):
 
 def test_checkpoint_resume(emu_lib):
     pc.check_checkpoint_resume(emu_lib)
+
+
+def test_post_chain(emu_lib):
+    pc.check_post_chain(emu_lib)

@@ -213,3 +213,7 @@ def test_against_golden_fixtures(product_lib):
 
 def test_checkpoint_resume(product_lib):
     pc.check_checkpoint_resume(product_lib)
+
+
+def test_post_chain(product_lib):
+    pc.check_post_chain(product_lib)
