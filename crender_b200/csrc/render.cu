@@ -301,7 +301,7 @@ namespace crb
         __global__ void __launch_bounds__(256) k_shade(DScene sc, RenderParams rp, PathState ps)
         {
             const uint32_t c0 = ps.counters[CTR_CLASS0], c1 = c0 + ps.counters[CTR_CLASS0 + 1], c2 = c1 + ps.counters[CTR_CLASS0 + 2],
-                           n = c2 + ps.counters[CTR_CLASS0 + 3];
+                           n = ps.sorted ? c2 + ps.counters[CTR_CLASS0 + 3] : ps.counters[CTR_IN];
             const uint32_t i = rp.bounce;
             for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
             {
@@ -311,8 +311,18 @@ namespace crb
                 ShadowRay      sr;
                 if (idx < n)
                 {
-                    const int cls = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
-                    slot          = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
+                    int cls;
+                    if (ps.sorted)
+                    {
+                        cls  = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
+                        slot = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
+                    }
+                    else
+                    {
+                        // unsorted mode: paths are shaded in queue (= screen) order
+                        slot = ps.q_in[idx];
+                        cls  = __float_as_uint(ps.hit[slot].w) == INVALID_PRIM ? 0 : 1;
+                    }
                     const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
                     const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
                     const float4 t4 = ps.thr[slot];
@@ -749,6 +759,11 @@ namespace crb
         ps.trace_chunk = trace_chunk;
         static const int postpone = getenv("CRB_POSTPONE") ? atoi(getenv("CRB_POSTPONE")) : 1;    // tuning knob; measured best = 1 (profiles/r1c_sweeps.md)
         ps.postpone = postpone;
+        // material sort before shading: implemented (k_classify + per-class queues) but OFF by default — the
+        // reference's shading is a few dozen instructions, k_shade is HBM-bound, and shading in queue (= screen)
+        // order keeps its gathers coalesced: measured 2598 vs 2409 Mrays/s (profiles/r1c_sweeps.md §12)
+        static const int sort_env = getenv("CRB_SORT") ? atoi(getenv("CRB_SORT")) : -1;
+        ps.sorted = sort_env >= 0 ? sort_env : ((flags & CRB_RENDER_FLAG_MATERIAL_SORT) ? 1 : 0);
 
         RenderParams rp {};
         rp.w = w, rp.h = h, rp.row0 = row0, rp.nrows = nrows, rp.npix = npix, rp.seed = seed;
@@ -797,10 +812,10 @@ namespace crb
                     CRB_LAUNCH((k_trace<false, 4>), pgrid, pblock, st, dscene, ps);
                 tock();
                 tick(CRB_K_SHADE);
-                CRB_LAUNCH(k_classify, pgrid, pblock, st, dscene, ps);
+                if (ps.sorted) CRB_LAUNCH(k_classify, pgrid, pblock, st, dscene, ps);
                 CRB_LAUNCH(k_shade, pgrid, pblock, st, dscene, rp, ps);
                 tock();
-                launches += 3;
+                launches += ps.sorted ? 3 : 2;
                 if (dscene.sun.enabled)
                 {
                     tick(CRB_K_SHADOW);

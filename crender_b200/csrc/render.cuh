@@ -28,6 +28,7 @@ namespace crb
         unsigned long long *stats;    // see ST_* below
         uint32_t  trace_chunk;        // work-reservation granularity of the persistent trace loop (0 = exact)
         int       postpone;           // lanes with waiting triangles needed before a warp runs a leaf test
+        int       sorted;             // 1: k_classify sorts paths by shade class before k_shade; 0: shade in queue order
     };
     enum { CTR_IN = 0, CTR_CLASS0 = 1, CTR_NEXT = 5, CTR_SHADOW = 6, CTR_CUR_TRACE = 7, CTR_CUR_SHADE = 8, CTR_CUR_SHADOW = 9, CTR_COUNT = 16 };
     enum { ST_CLOSEST = 0, ST_SHADOW = 1, ST_RANOUT = 2, ST_NODES = 3, ST_TRIS = 4, ST_NODES_SHADOW = 5, ST_TRIS_SHADOW = 6, ST_COUNT = 8 };

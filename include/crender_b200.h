@@ -185,7 +185,8 @@ int crb_microbench_read(crb_scene *, uint64_t bytes, int iters, double *gb_per_s
 int crb_last_query_ms(crb_scene *, double *ms);
 
 /* ---- renderer: cr::renderer (src/render/renderer.h:24-105) */
-enum { CRB_RENDER_FLAG_COUNTERS = 1, CRB_RENDER_FLAG_TIMERS = 2 };
+/* CRB_RENDER_FLAG_MATERIAL_SORT: sort the traced paths by shade class (miss/metal/smooth/glass) before shading */
+enum { CRB_RENDER_FLAG_COUNTERS = 1, CRB_RENDER_FLAG_TIMERS = 2, CRB_RENDER_FLAG_MATERIAL_SORT = 4 };
 /* renderer::renderer(res_x,res_y,bounces,pool,scene) (renderer.cpp:106-145) + set_resolution's aspect
  * (renderer.cpp:194-208). seed keys the counter-based sampler (DESIGN.md "Sampler"). */
 int crb_render_create(crb_scene *, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags, crb_render **out);

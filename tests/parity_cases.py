@@ -317,3 +317,20 @@ def check_post_chain(lib_path):
     r.render(2)
     kw = dict(use_tonemapping=True, tonemapping_type=3, use_bloom=True)
     np.testing.assert_allclose(r.post_process(api.post_settings(**kw)), post_oracle.process(r.current_progress(), **kw), rtol=2e-5, atol=2e-6)
+
+
+def check_material_sort_is_equivalent(lib_path):
+    """The optional material sort (k_classify) only reorders work: accumulated sums are bit-identical."""
+    desc = scenes.textured_scene()
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    a = api.renderer(80, 60, 6, g, seed=4, material_sort=False)
+    b = api.renderer(80, 60, 6, g, seed=4, material_sort=True)
+    a.render(4)
+    b.render(4)
+    np.testing.assert_array_equal(a.raw_sum(), b.raw_sum())
+    np.testing.assert_array_equal(a.current_normals(), b.current_normals())
+    sa, sb = a.current_stats(), b.current_stats()
+    assert sa.total_queries == sb.total_queries and sa.ref_rays == sb.ref_rays
+    assert sb.kernel_launches > sa.kernel_launches  # the sort is an extra pass per bounce

@@ -45,3 +45,7 @@ def test_checkpoint_resume(emu_lib):
 
 def test_post_chain(emu_lib):
     pc.check_post_chain(emu_lib)
+
+
+def test_material_sort_is_equivalent(emu_lib):
+    pc.check_material_sort_is_equivalent(emu_lib)

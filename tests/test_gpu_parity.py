@@ -217,3 +217,7 @@ def test_checkpoint_resume(product_lib):
 
 def test_post_chain(product_lib):
     pc.check_post_chain(product_lib)
+
+
+def test_material_sort_is_equivalent(product_lib):
+    pc.check_material_sort_is_equivalent(product_lib)
