@@ -298,7 +298,7 @@ namespace crb
             return v3(cosf(phi) * sin_theta, cos_theta, sinf(phi) * sin_theta);
         }
 
-        __global__ void __launch_bounds__(256) k_shade(DScene sc, RenderParams rp, PathState ps)
+        __global__ void __launch_bounds__(256, 4) k_shade(DScene sc, RenderParams rp, PathState ps)
         {
             const uint32_t c0 = ps.counters[CTR_CLASS0], c1 = c0 + ps.counters[CTR_CLASS0 + 1], c2 = c1 + ps.counters[CTR_CLASS0 + 2],
                            n = ps.sorted ? c2 + ps.counters[CTR_CLASS0 + 3] : ps.counters[CTR_IN];
