@@ -99,15 +99,24 @@ namespace crb
         const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
         const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
                     sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
-        const unsigned imask = n0.w >> 24;
         const float    ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
         const float    bx = (px - o.x) * idir.x, by = (py - o.y) * idir.y, bz = (pz - o.z) * idir.z;
         const bool     nx = idir.x < 0.0f, ny = idir.y < 0.0f, nz = idir.z < 0.0f;
-        unsigned       hits = 0;
+        // inner children sit at priority bit 24 + (slot ^ octinv): their meta byte already holds 24 + slot,
+        // so the ray octant is folded in with one XOR on four bytes at a time (inner <=> bits 3 and 4 of the
+        // byte are set; leaf offsets are < 24). NOTE: an earlier per-slot form `inner ? 24 + (slot ^ octinv)
+        // : meta & 31` was miscompiled by ptxas 12.9 (the loop-invariant arm was hoisted out of the STEPS loop
+        // into a register that the predicated other arm then overwrote); keep the index
+        // computation free of loop-invariant select arms.
+        const unsigned octinv4 = octinv * 0x01010101u;
+        unsigned       hits    = 0;
 #pragma unroll
         for (int half = 0; half < 2; half++)
         {
-            const unsigned meta4 = half ? n1.w : n1.z;
+            const unsigned meta4      = half ? n1.w : n1.z;
+            const unsigned is_inner4  = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const unsigned index4     = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu))) & 0x1f1f1f1fu;
+            const unsigned childbits4 = (meta4 >> 5) & 0x07070707u;
             const unsigned lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
             const unsigned hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
             const unsigned nearx = nx ? hix : lox, farx = nx ? lox : hix;
@@ -116,18 +125,14 @@ namespace crb
 #pragma unroll
             for (int j = 0; j < 4; j++)
             {
-                const unsigned meta = byte_of(meta4, j);
                 const float    t0x = fmaf(float(byte_of(nearx, j)), ax, bx), t1x = fmaf(float(byte_of(farx, j)), ax, bx);
                 const float    t0y = fmaf(float(byte_of(neary, j)), ay, by), t1y = fmaf(float(byte_of(fary, j)), ay, by);
                 const float    t0z = fmaf(float(byte_of(nearz, j)), az, bz), t1z = fmaf(float(byte_of(farz, j)), az, bz);
                 const float    tn  = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
                 const float    tf  = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-                // branch-free: inner children sit at priority bit 24 + (slot ^ octinv), leaves contribute
-                // their unary triangle count at their triangle offset; an empty slot has meta == 0 -> 0 bits
-                const int      slot  = half * 4 + j;
-                const bool     inner = (imask >> slot) & 1u;
-                const unsigned index = inner ? (24u + (unsigned(slot) ^ octinv)) : (meta & 31u);
-                const unsigned bits  = (meta >> 5) << index;
+                // branch-free: leaves contribute their unary triangle count at their triangle offset, inner
+                // children one bit at their priority; an empty slot has meta == 0 -> 0 bits
+                const unsigned bits = byte_of(childbits4, j) << byte_of(index4, j);
                 hits |= (tn <= tf * BVH8_BOX_SLACK) ? bits : 0u;
             }
         }
@@ -209,8 +214,10 @@ namespace crb
     //
     //   source(idx, item, o, d, tmin, tmax)  loads work item idx (called by the lane that owns it)
     //   sink(valid, item, hit)               called by ALL lanes at a convergent point; valid lanes retire
-    template<bool ANY, bool COUNT, int STEPS, typename Source, typename Sink>
-    __device__ __forceinline__ void trace_persistent(const Bvh8 &bvh, uint32_t *cursor, uint32_t n, uint32_t chunk_max, int postpone, Source source, Sink sink,
+    // `any` (any-hit vs closest-hit) is a RUN-TIME argument on purpose: both query kinds execute the same
+    // compiled loop, so the bit-exact closest-hit parity tests cover the code any-hit queries run.
+    template<bool COUNT, int STEPS, typename Source, typename Sink>
+    __device__ __forceinline__ void trace_persistent(const Bvh8 &bvh, uint32_t *cursor, uint32_t n, uint32_t chunk_max, bool any, Source source, Sink sink,
                                                      TravCounters *ctr)
     {
         const unsigned FULL = 0xffffffffu;
@@ -302,13 +309,11 @@ namespace crb
                     group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
                     tgroup           = make_uint2(n1.y, h & 0x00ffffffu);
                 }
-                // ---- triangle phase, postponed until enough lanes have triangles waiting: a leaf test
-                // issued for 2-3 lanes costs the same issue slots as one issued for 16 (measured: the
-                // un-postponed triangle loop was 52 % of k_trace's instructions at 2.7 active lanes)
-                const bool     pending = active && tgroup.y != 0u;
-                const unsigned pm      = __ballot_sync(FULL, pending);
-                const unsigned nm      = __ballot_sync(FULL, active && !pending);
-                if (pm != 0u && (__popc(pm) >= postpone || nm == 0u))
+                // ---- leaf phase in lock step: ONE triangle per lane that has triangles waiting (an inner
+                // per-lane triangle loop was 52 % of k_trace's instructions at 2.7 active lanes; waiting for
+                // more lanes to have triangles was measured and is slower, profiles/r1c_sweeps.md §6)
+                const bool pending = active && tgroup.y != 0u;
+                if (__ballot_sync(FULL, pending) != 0u)
                 {
                     if (pending)
                     {
@@ -321,17 +326,15 @@ namespace crb
                         if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, best.t, t, u, v))
                         {
                             const unsigned prim = __float_as_uint(a.w);
-                            if (ANY)
+                            if (t < best.t || prim < best.prim) best = Hit { t, u, v, prim };
+                            if (any)
                             {
                                 // any hit ends the query: drop all remaining work, the advance step below
                                 // retires the ray (single retire point for both query kinds)
-                                best     = Hit { t, u, v, prim };
                                 group.y  = 0u;
                                 tgroup.y = 0u;
                                 sp       = 0;
                             }
-                            else if (t < best.t || prim < best.prim)
-                                best = Hit { t, u, v, prim };
                         }
                     }
                 }

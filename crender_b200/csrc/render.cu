@@ -197,7 +197,7 @@ namespace crb
             auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
                 if (valid) ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
             };
-            trace_persistent<false, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_TRACE, n, ps.trace_chunk, ps.postpone, source, sink, &tc);
+            trace_persistent<COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_TRACE, n, ps.trace_chunk, false, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES, tc.nodes);
@@ -474,7 +474,7 @@ namespace crb
                     ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
                 }
             };
-            trace_persistent<true, COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_SHADOW, n, ps.trace_chunk, ps.postpone, source, sink, &tc);
+            trace_persistent<COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_SHADOW, n, ps.trace_chunk, true, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES_SHADOW, tc.nodes);
@@ -757,8 +757,6 @@ namespace crb
         ps.shadow = shadow.p, ps.counters = counters.p, ps.stats = dstats.p;
         static const uint32_t trace_chunk = getenv("CRB_TRACE_CHUNK") ? uint32_t(atoi(getenv("CRB_TRACE_CHUNK"))) : 0u;    // tuning knob
         ps.trace_chunk = trace_chunk;
-        static const int postpone = getenv("CRB_POSTPONE") ? atoi(getenv("CRB_POSTPONE")) : 1;    // tuning knob; measured best = 1 (profiles/r1c_sweeps.md)
-        ps.postpone = postpone;
         // material sort before shading: implemented (k_classify + per-class queues) but OFF by default — the
         // reference's shading is a few dozen instructions, k_shade is HBM-bound, and shading in queue (= screen)
         // order keeps its gathers coalesced: measured 2598 vs 2409 Mrays/s (profiles/r1c_sweeps.md §12)

@@ -27,7 +27,6 @@ namespace crb
         uint32_t  *counters;    // see CTR_* below
         unsigned long long *stats;    // see ST_* below
         uint32_t  trace_chunk;        // work-reservation granularity of the persistent trace loop (0 = exact)
-        int       postpone;           // lanes with waiting triangles needed before a warp runs a leaf test
         int       sorted;             // 1: k_classify sorts paths by shade class before k_shade; 0: shade in queue order
     };
     enum { CTR_IN = 0, CTR_CLASS0 = 1, CTR_NEXT = 5, CTR_SHADOW = 6, CTR_CUR_TRACE = 7, CTR_CUR_SHADE = 8, CTR_CUR_SHADOW = 9, CTR_COUNT = 16 };

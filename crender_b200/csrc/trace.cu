@@ -29,7 +29,7 @@ namespace crb
         // persistent kernels: each warp is a pool of 32 traversal lanes refilled from `cursor` (bvh8.cuh)
         template<bool COUNT>
         __global__ void __launch_bounds__(256, 4) k_intersect_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits,
-                                                                 uint32_t *cursor, unsigned long long *ctr, int postpone)
+                                                                 uint32_t *cursor, unsigned long long *ctr)
         {
             TravCounters tc;
             auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
@@ -45,7 +45,7 @@ namespace crb
                 if (h.prim != INVALID_PRIM) resolve_flat(sc, h.prim, out.prim, out.model, out.inst);
                 hits[item] = out;
             };
-            trace_persistent<false, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, postpone, source, sink, &tc);
+            trace_persistent<COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, false, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ctr + 0, tc.nodes);
@@ -55,7 +55,7 @@ namespace crb
 
         template<bool COUNT>
         __global__ void __launch_bounds__(256, 4) k_occluded_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, uint8_t *__restrict__ occ,
-                                                                uint32_t *cursor, unsigned long long *ctr, int postpone)
+                                                                uint32_t *cursor, unsigned long long *ctr)
         {
             TravCounters tc;
             auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
@@ -66,7 +66,7 @@ namespace crb
             auto sink = [&](bool valid, uint32_t item, const Hit &h) {
                 if (occ && valid) occ[item] = h.prim != INVALID_PRIM ? 1 : 0;
             };
-            trace_persistent<true, COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, postpone, source, sink, &tc);
+            trace_persistent<COUNT, BATCH_STEPS>(sc.bvh, cursor, n, 0u, true, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ctr + 0, tc.nodes);
@@ -123,7 +123,6 @@ namespace crb
             const size_t out_elem = mode == 0 ? sizeof(crb_hit) : 1;
             DBuf<float4> d_rays;
             DBuf<char>   d_out;
-            const int    B = 256;
             for (uint64_t off = 0; off < n; off += CHUNK)
             {
                 const uint64_t cnt = std::min<uint64_t>(CHUNK, n - off);
@@ -144,18 +143,17 @@ namespace crb
 #ifdef CRB_EMU
                 const unsigned g = 1, blk = 1;
 #else
-                const unsigned g = unsigned(s.n_sms) * 4, blk = B;
+                const unsigned g = unsigned(s.n_sms) * 4, blk = 256;
 #endif
                 const uint32_t cnt32 = uint32_t(cnt);
-                static const int postpone = getenv("CRB_POSTPONE") ? atoi(getenv("CRB_POSTPONE")) : 1;    // tuning knob
                 dev_zero(d_cursor.p, 4, s.stream);
                 timer.start();
                 switch (mode)
                 {
-                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), d_cursor.p, d_ctr.p, postpone); break;
-                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<uint8_t *>(op), d_cursor.p, d_ctr.p, postpone); break;
-                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, blk, s.stream, sc, rp, cnt32, (crb_hit *) nullptr, d_cursor.p, d_ctr.p, postpone); break;
-                default: CRB_LAUNCH((k_occluded_batch<true>), g, blk, s.stream, sc, rp, cnt32, (uint8_t *) nullptr, d_cursor.p, d_ctr.p, postpone); break;
+                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), d_cursor.p, d_ctr.p); break;
+                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<uint8_t *>(op), d_cursor.p, d_ctr.p); break;
+                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, blk, s.stream, sc, rp, cnt32, (crb_hit *) nullptr, d_cursor.p, d_ctr.p); break;
+                default: CRB_LAUNCH((k_occluded_batch<true>), g, blk, s.stream, sc, rp, cnt32, (uint8_t *) nullptr, d_cursor.p, d_ctr.p); break;
                 }
                 ms += timer.stop();
                 if (!on_device && mode < 2) dev_download(static_cast<char *>(out) + off * out_elem, d_out.p, cnt * out_elem, s.stream);

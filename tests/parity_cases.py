@@ -334,3 +334,73 @@ def check_material_sort_is_equivalent(lib_path):
     sa, sb = a.current_stats(), b.current_stats()
     assert sa.total_queries == sb.total_queries and sa.ref_rays == sb.ref_rays
     assert sb.kernel_launches > sa.kernel_launches  # the sort is an extra pass per bounce
+
+
+def check_query_kinds_consistent(lib_path, desc, n_rays=400000, seeds=(21, 22, 23)):
+    """Any-hit and closest-hit queries are separate kernel instantiations of the same traversal loop: for
+    every ray `occluded` must equal `closest hit exists`. 400k rays x 3 seeds per scene: the ptxas
+    miscompile recorded in DESIGN.md section 4 affected 5e-5 .. 6e-3 of the rays of ONE instantiation, so
+    small ray counts do not find this class of error. Also checks the counting instantiations through the
+    property that stopping at the first hit can never visit more than the closest-hit traversal."""
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    for seed in seeds:
+        rays = common.mixed_rays(desc, n_rays, seed=seed)
+        hit = g.cast_rays(rays)["prim"] != common.MISS
+        occ = g.occluded(rays).astype(bool)
+        assert int((occ != hit).sum()) == 0, (seed, int((occ != hit).sum()))
+    sub = rays[:: max(1, n_rays // 20000)]
+    nc, tc = g.trace_counters(sub, any_hit=False)
+    na, ta = g.trace_counters(sub, any_hit=True)
+    assert 0 < na <= nc and 0 < ta <= tc, (na, nc, ta, tc)
+    # per-ray version of the same property on a handful of rays that hit something
+    for i in np.nonzero(hit[:: max(1, n_rays // 20000)])[0][:16]:
+        c, a = g.trace_counters(sub[i : i + 1], any_hit=False), g.trace_counters(sub[i : i + 1], any_hit=True)
+        assert a[0] <= c[0] and a[1] <= c[1], (int(i), a, c)
+
+
+def check_instrumented_render_is_identical(lib_path):
+    """The counting / timing instantiations of the wavefront kernels (k_trace<true>, k_shadow<true>) must
+    produce the same image, bit for bit, as the plain ones, and their query counts must match."""
+    desc = scenes.terrain_city(24, 2, n_buildings=12)
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    a = api.renderer(160, 90, 5, g, seed=9)
+    b = api.renderer(160, 90, 5, g, seed=9, counters=True, timers=True)
+    a.render(6)
+    b.render(6)
+    np.testing.assert_array_equal(a.raw_sum(), b.raw_sum())
+    np.testing.assert_array_equal(a.current_depths(), b.current_depths())
+    sb = b.current_stats()
+    assert sb.total_queries > 0 and sb.node_visits[0] > 0 and sb.tri_tests[0] > 0
+
+
+RENDER_HASH_SNIPPET = r"""
+import sys, hashlib
+sys.path.insert(0, {root!r})
+from crender_b200 import api, scenes
+desc = scenes.terrain_city(24, 2, n_buildings=12)
+g = api.scene(lib_path={lib!r}); scenes.load(desc, g); g.commit()
+r = api.renderer(160, 90, 5, g, seed=9); r.render(6)
+print("HASH", hashlib.sha256(r.raw_sum().tobytes()).hexdigest())
+"""
+
+
+def check_trace_steps_variants_identical(lib_path):
+    """k_trace / k_shadow are instantiated for 1, 2, 4 and 8 traversal steps per refill check (tuning knob
+    CRB_TRACE_STEPS, read once per process): every instantiation must give the same accumulated sums."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = RENDER_HASH_SNIPPET.format(root=root, lib=lib_path)
+    hashes = {}
+    for steps in ("1", "2", "4", "8"):
+        env = dict(os.environ, CRB_TRACE_STEPS=steps)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes[steps] = [ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][0]
+    assert len(set(hashes.values())) == 1, hashes

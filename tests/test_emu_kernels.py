@@ -49,3 +49,11 @@ def test_post_chain(emu_lib):
 
 def test_material_sort_is_equivalent(emu_lib):
     pc.check_material_sort_is_equivalent(emu_lib)
+
+
+def test_query_kinds_consistent(emu_lib):
+    pc.check_query_kinds_consistent(emu_lib, common.small_scenes()["terrain"], n_rays=6000, seeds=(21,))
+
+
+def test_instrumented_render_is_identical(emu_lib):
+    pc.check_instrumented_render_is_identical(emu_lib)

@@ -221,3 +221,16 @@ def test_post_chain(product_lib):
 
 def test_material_sort_is_equivalent(product_lib):
     pc.check_material_sort_is_equivalent(product_lib)
+
+
+@pytest.mark.parametrize("name", ["cornell", "mesh", "textured", "terrain"])
+def test_query_kinds_consistent(product_lib, name):
+    pc.check_query_kinds_consistent(product_lib, common.small_scenes()[name])
+
+
+def test_instrumented_render_is_identical(product_lib):
+    pc.check_instrumented_render_is_identical(product_lib)
+
+
+def test_trace_steps_variants_identical(product_lib):
+    pc.check_trace_steps_variants_identical(product_lib)
