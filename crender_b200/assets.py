@@ -6,7 +6,7 @@ Mirrors cr::asset_loader (src/util/asset_loader.cpp):
   export_framebuffer  :348-377  ./out/<name><ext>, " (n)" suffix when the file exists
   export_png / jpg    :89-110   byte = min(x*255, 255) on all four channels, JPG quality 100
   export_hdr          :172-178  pow(x, 2.2) then Radiance RGBE
-  export_exr          :112-170  3 half channels in B,G,R order (not implemented here: no EXR writer in the image)
+  export_exr          :112-170  3 half channels in B,G,R order, ZIP blocks (own writer; tinyexr is not in the image)
 Nothing here is on the measured path; it is plain numpy/PIL host code.
 """
 from __future__ import annotations
@@ -153,6 +153,116 @@ def read_hdr(path: str) -> np.ndarray:
     return a[..., :3].astype(np.float32) * scale[..., None]
 
 
+def _float_to_half_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> IEEE half bit patterns the way tinyexr's float_to_half_full does it (the reference stores
+    HALF channels, asset_loader.cpp:158-162): mantissa truncated to 10 bits, +1 when the first dropped bit is
+    set (round half up in magnitude, not ties-to-even), overflow -> inf, tiny -> signed zero/denormal."""
+    f = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.int64)
+    sign = (f >> 31) & 1
+    exp = (f >> 23) & 0xFF
+    man = f & 0x7FFFFF
+    newexp = exp - 127 + 15
+    out = np.zeros(f.shape, np.int64)
+    infnan = exp == 255
+    out = np.where(infnan, (31 << 10) | np.where(man != 0, 0x200, 0), out)
+    over = (~infnan) & (exp != 0) & (newexp >= 31)
+    out = np.where(over, 31 << 10, out)
+    norm = (~infnan) & (exp != 0) & (newexp > 0) & (newexp < 31)
+    out = np.where(norm, ((newexp << 10) | (man >> 13)) + ((man >> 12) & 1), out)
+    under = (~infnan) & (exp != 0) & (newexp <= 0) & ((14 - newexp) <= 24)
+    sh = np.clip(14 - newexp, 0, 62)
+    mant = man | 0x800000
+    out = np.where(under, (mant >> sh) + ((mant >> np.clip(sh - 1, 0, 62)) & 1), out)
+    return ((sign << 15) | (out & 0x7FFF)).astype(np.uint16)
+
+
+def _exr_attr(name: str, typ: str, value: bytes) -> bytes:
+    return name.encode() + b"\0" + typ.encode() + b"\0" + np.int32(len(value)).tobytes() + value
+
+
+def _write_exr(path: str, rgba: np.ndarray):
+    """OpenEXR 2 single-part scanline file, three HALF channels named B, G, R (the reference's order,
+    asset_loader.cpp:135-161), ZIP compression in 16-line blocks (tinyexr's default). The pixel values decode
+    to exactly what the reference's file decodes to; the deflate stream itself comes from zlib, not miniz."""
+    import zlib
+
+    h, w = rgba.shape[:2]
+    half = _float_to_half_bits(rgba[..., :3])  # (h, w, 3) as R, G, B
+    chl = b""
+    for ch in (b"B", b"G", b"R"):
+        chl += ch + b"\0" + np.int32(1).tobytes() + b"\0\0\0\0" + np.int32(1).tobytes() + np.int32(1).tobytes()
+    chl += b"\0"
+    box = np.array([0, 0, w - 1, h - 1], np.int32).tobytes()
+    head = b"\x76\x2f\x31\x01" + np.int32(2).tobytes()
+    head += _exr_attr("channels", "chlist", chl)
+    head += _exr_attr("compression", "compression", bytes([3]))  # ZIP_COMPRESSION
+    head += _exr_attr("dataWindow", "box2i", box)
+    head += _exr_attr("displayWindow", "box2i", box)
+    head += _exr_attr("lineOrder", "lineOrder", bytes([0]))  # INCREASING_Y
+    head += _exr_attr("pixelAspectRatio", "float", np.float32(1).tobytes())
+    head += _exr_attr("screenWindowCenter", "v2f", np.zeros(2, np.float32).tobytes())
+    head += _exr_attr("screenWindowWidth", "float", np.float32(1).tobytes())
+    head += b"\0"
+    chunks = []
+    for y0 in range(0, h, 16):
+        rows = half[y0 : y0 + 16]
+        raw = np.ascontiguousarray(rows[:, :, ::-1].transpose(0, 2, 1)).astype("<u2").tobytes()  # per line: B row, G row, R row
+        a = np.frombuffer(raw, np.uint8)
+        re = np.concatenate([a[0::2], a[1::2]]).astype(np.int32)  # even bytes, then odd bytes
+        pred = re.copy()
+        pred[1:] = (re[1:] - re[:-1] + 128 + 256) & 255
+        comp = zlib.compress(pred.astype(np.uint8).tobytes())
+        data = comp if len(comp) < len(raw) else raw
+        chunks.append(np.int32(y0).tobytes() + np.int32(len(data)).tobytes() + data)
+    off = len(head) + 8 * len(chunks)
+    table = b""
+    for c in chunks:
+        table += np.uint64(off).tobytes()
+        off += len(c)
+    with open(path, "wb") as f:
+        f.write(head + table + b"".join(chunks))
+
+
+def read_exr(path: str) -> np.ndarray:
+    """Minimal reader for the files _write_exr produces (test helper): returns (H, W, 3) float32 as R, G, B."""
+    import zlib
+
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"\x76\x2f\x31\x01"
+    pos, attrs = 8, {}
+    while raw[pos] != 0:
+        e = raw.index(b"\0", pos)
+        name = raw[pos:e].decode()
+        e2 = raw.index(b"\0", e + 1)
+        size = int(np.frombuffer(raw[e2 + 1 : e2 + 5], np.int32)[0])
+        attrs[name] = (raw[e + 1 : e2].decode(), raw[e2 + 5 : e2 + 5 + size])
+        pos = e2 + 5 + size
+    pos += 1
+    x0, y0, x1, y1 = np.frombuffer(attrs["dataWindow"][1], np.int32)
+    w, h = int(x1 - x0 + 1), int(y1 - y0 + 1)
+    names = [c for c in attrs["channels"][1].split(b"\0") if c in (b"B", b"G", b"R")]
+    assert names == [b"B", b"G", b"R"] and attrs["compression"][1] == bytes([3])
+    nblk = (h + 15) // 16
+    offs = np.frombuffer(raw[pos : pos + 8 * nblk], np.uint64)
+    out = np.zeros((h, w, 3), np.float32)
+    for o in offs:
+        o = int(o)
+        y, n = (int(v) for v in np.frombuffer(raw[o : o + 8], np.int32))
+        lines = min(16, h - y)
+        want = lines * w * 3 * 2
+        data = raw[o + 8 : o + 8 + n]
+        if n < want:
+            p = np.frombuffer(zlib.decompress(data), np.uint8).astype(np.int32)
+            p[1:] -= 128
+            re = (np.cumsum(p) & 255).astype(np.uint8)
+            a = np.empty(want, np.uint8)
+            a[0::2], a[1::2] = re[: (want + 1) // 2], re[(want + 1) // 2 :]
+            data = a.tobytes()
+        blk = np.frombuffer(data, "<u2").reshape(lines, 3, w).view(np.float16).astype(np.float32)
+        out[y : y + lines] = blk[:, ::-1, :].transpose(0, 2, 1)
+    return out
+
+
 def export_framebuffer(buffer: np.ndarray, path: str, image_type: str = PNG, out_dir: str = "./out/") -> str:
     """cr::asset_loader::export_framebuffer: writes `out_dir/path.ext`, or `path (n).ext` if it exists.
     buffer: (H, W, 4) float32, e.g. renderer.current_progress(). Returns the file written."""
@@ -174,5 +284,5 @@ def export_framebuffer(buffer: np.ndarray, path: str, image_type: str = PNG, out
     elif image_type == HDR:
         _write_hdr(target, np.asarray(buffer, np.float32))
     else:
-        raise NotImplementedError("EXR export needs an OpenEXR writer, which this image does not have (reference: tinyexr, B,G,R half channels)")
+        _write_exr(target, np.asarray(buffer, np.float32))
     return target

@@ -80,3 +80,32 @@ def test_export_png_jpg_hdr(tmp_path):
     expect = np.power(buf[..., :3], 2.2)
     # RGBE shares one exponent per pixel: absolute error up to max_component / 256 (truncating mantissa)
     assert np.all(np.abs(back - expect) <= expect.max(axis=-1, keepdims=True) / 128 + 1e-6)
+
+
+def test_export_exr(tmp_path):
+    # asset_loader.cpp:112-170: three HALF channels named B, G, R; tinyexr default = ZIP blocks of 16 lines
+    rng = np.random.default_rng(5)
+    h, w = 37, 23  # not a multiple of the 16-line block
+    img = rng.random((h, w, 4), dtype=np.float32) * 4.0
+    img[0, 0, :3] = (0.0, 65520.0, 1e-9)  # zero, overflow -> inf, underflow -> 0
+    img[0, 1, :3] = (np.float32(1.0) + np.float32(2.0**-11), 6e-6, -2.5)  # tie rounds up in magnitude; denormal half; sign
+    path = assets.export_framebuffer(img, "frame", assets.EXR, out_dir=str(tmp_path))
+    assert path.endswith("frame.exr")
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x76\x2f\x31\x01\x02\x00\x00\x00"
+    assert raw.index(b"channels\0chlist\0") == 8
+    chl = raw[raw.index(b"chlist\0") + 11 :]
+    assert chl[:2] == b"B\0" and chl[18:20] == b"G\0" and chl[36:38] == b"R\0"  # (A)BGR order, pixel type 1 = HALF
+    assert chl[2:6] == b"\x01\0\0\0"
+    back = assets.read_exr(path)
+    assert back.shape == (h, w, 3)
+    with np.errstate(over="ignore"):
+        want = img[..., :3].astype(np.float16).astype(np.float32)
+    # identical to IEEE round-to-nearest except exact ties, which tinyexr rounds away from zero
+    ties = (img[..., :3].view(np.uint32) & 0x1FFF) == 0x1000
+    np.testing.assert_array_equal(back[~ties], want[~ties])
+    assert back[0, 0, 0] == 0.0 and np.isinf(back[0, 0, 1]) and back[0, 0, 2] == 0.0
+    assert back[0, 1, 0] == np.float32(1.0) + np.float32(2.0**-10)
+    assert back[0, 1, 2] == -2.5 and abs(back[0, 1, 1] - 6e-6) < 6e-8
+    # second export of the same name gets the " (1)" suffix like every other format
+    assert assets.export_framebuffer(img, "frame", assets.EXR, out_dir=str(tmp_path)).endswith("frame (1).exr")
