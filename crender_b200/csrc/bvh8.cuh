@@ -26,10 +26,6 @@
 
 namespace crb
 {
-#ifndef CRB_NODE256
-#define CRB_NODE256 0
-#endif
-    constexpr int      BVH8_NODE_U4    = CRB_NODE256 ? 6 : 5;    // node stride in 16-byte units
     constexpr int      BVH8_STACK      = 48;     // entries; the builder rejects deeper trees loudly
     constexpr int      BVH8_LEAF_TRIS  = 3;      // max triangles per leaf child
     constexpr uint32_t INVALID_PRIM    = 0xffffffffu;
@@ -81,22 +77,6 @@ namespace crb
 
     __device__ __forceinline__ unsigned byte_of(unsigned w, int i) { return (w >> (8 * i)) & 0xffu; }
 
-#ifndef CRB_U8CVT
-#define CRB_U8CVT 0
-#endif
-    // float(byte i of w), exact. The plain conversion is an I2F on the quarter-rate XU pipe and the node test
-    // needs 48 of them, which made XU the busiest pipe of k_trace (ncu: 65 %); splicing the byte into the
-    // mantissa of 2^23 (one PRMT on the ALU pipe) and subtracting 2^23 (one FADD on the FMA pipe) gives the
-    // same value.
-    __device__ __forceinline__ float u8_to_float(unsigned w, int i)
-    {
-#if !defined(CRB_EMU) && CRB_U8CVT == 1
-        return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7650u | unsigned(i))), 8388608.0f);
-#else
-        return float(byte_of(w, i));
-#endif
-    }
-
     // 16-byte read-only load that the compiler may not sink below later branches: the three loads of a
     // triangle record must be in flight together (ncu showed the v0 load issued after the det test,
     // i.e. two serialised L2 round trips per leaf test)
@@ -108,109 +88,6 @@ namespace crb
         float4 v;
         asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
         return v;
-#endif
-    }
-
-#ifndef CRB_L2HINT
-#define CRB_L2HINT 0
-#endif
-    // BVH loads of the persistent traversal loop carry an L2 evict_last policy: the tree (58 MB for the
-    // 1M-triangle scene) fits B200's L2, but the ray / hit / path-state queues streaming through the same L2
-    // evict parts of it, and every such miss is an HBM round trip in a chain of dependent loads.
-    __device__ __forceinline__ unsigned long long l2_keep_policy()
-    {
-#if !defined(CRB_EMU) && CRB_L2HINT
-        unsigned long long pol;
-        asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-        return pol;
-#else
-        return 0ull;
-#endif
-    }
-    __device__ __forceinline__ uint4 ld_node16(const uint4 *p, unsigned long long pol)
-    {
-#if !defined(CRB_EMU) && CRB_L2HINT
-        uint4 v;
-        asm("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-        return v;
-#else
-        (void) pol;
-        return __ldg(p);
-#endif
-    }
-    __device__ __forceinline__ void ld_node32(const uint4 *p, uint4 &a, uint4 &b)
-    {
-#if !defined(CRB_EMU)
-        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-            : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-            : "l"(p));
-#else
-        a = p[0], b = p[1];
-#endif
-    }
-    __device__ __forceinline__ float4 ld_tri16(const float4 *p, unsigned long long pol)
-    {
-#if !defined(CRB_EMU) && CRB_L2HINT
-        float4 v;
-        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-        return v;
-#else
-        (void) pol;
-        return ldg128_pinned(p);
-#endif
-    }
-
-#ifndef CRB_PREFETCH
-#define CRB_PREFETCH 0
-#endif
-    // Hint: bring the 80-byte record of the node that will be visited next towards the SM while the warp is
-    // busy with the leaf phase (the traversal is a chain of dependent loads).
-    __device__ __forceinline__ void prefetch_node(const uint4 *p)
-    {
-#if !defined(CRB_EMU) && CRB_PREFETCH == 1
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 4));
-#elif !defined(CRB_EMU) && CRB_PREFETCH == 2
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 4));
-#elif !defined(CRB_EMU) && CRB_PREFETCH == 3
-        unsigned d0, d1;
-        asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(d0) : "l"(p));
-        asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(d1) : "l"(p + 4));
-#else
-        (void) p;
-#endif
-    }
-
-#ifndef CRB_F32X2
-#define CRB_F32X2 1
-#endif
-    // (q0, q1) * a + b with one rounding each, as ONE instruction: sm_100 has packed-pair FP32 arithmetic
-    // (FFMA2 / FMUL2; scalar operands are broadcast for free). k_trace is bound by instruction issue, and the
-    // slab test is 48 FMAs per node, so pairing neighbouring children halves that part. Same values as fmaf.
-    __device__ __forceinline__ void fma_pair(float q0, float q1, float a, float b, float &r0, float &r1)
-    {
-#if !defined(CRB_EMU) && CRB_F32X2
-        unsigned long long q, aa, bb, r;
-        asm("mov.b64 %0, {%1,%2};" : "=l"(q) : "f"(q0), "f"(q1));
-        asm("mov.b64 %0, {%1,%1};" : "=l"(aa) : "f"(a));
-        asm("mov.b64 %0, {%1,%1};" : "=l"(bb) : "f"(b));
-        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(q), "l"(aa), "l"(bb));
-        asm("mov.b64 {%0,%1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
-#else
-        r0 = fmaf(q0, a, b), r1 = fmaf(q1, a, b);
-#endif
-    }
-    __device__ __forceinline__ void mul_pair(float q0, float q1, float a, float &r0, float &r1)
-    {
-#if !defined(CRB_EMU) && CRB_F32X2
-        unsigned long long q, aa, r;
-        asm("mov.b64 %0, {%1,%2};" : "=l"(q) : "f"(q0), "f"(q1));
-        asm("mov.b64 %0, {%1,%1};" : "=l"(aa) : "f"(a));
-        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(q), "l"(aa));
-        asm("mov.b64 {%0,%1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
-#else
-        r0 = q0 * a, r1 = q1 * a;
 #endif
     }
 
@@ -246,30 +123,17 @@ namespace crb
             const unsigned neary = ny ? hiy : loy, fary = ny ? loy : hiy;
             const unsigned nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
 #pragma unroll
-            for (int jp = 0; jp < 4; jp += 2)
+            for (int j = 0; j < 4; j++)
             {
-                float t0x[2], t1x[2], t0y[2], t1y[2], t0z[2], t1z[2], tn[2], tf[2];
-                fma_pair(u8_to_float(nearx, jp), u8_to_float(nearx, jp + 1), ax, bx, t0x[0], t0x[1]);
-                fma_pair(u8_to_float(farx, jp), u8_to_float(farx, jp + 1), ax, bx, t1x[0], t1x[1]);
-                fma_pair(u8_to_float(neary, jp), u8_to_float(neary, jp + 1), ay, by, t0y[0], t0y[1]);
-                fma_pair(u8_to_float(fary, jp), u8_to_float(fary, jp + 1), ay, by, t1y[0], t1y[1]);
-                fma_pair(u8_to_float(nearz, jp), u8_to_float(nearz, jp + 1), az, bz, t0z[0], t0z[1]);
-                fma_pair(u8_to_float(farz, jp), u8_to_float(farz, jp + 1), az, bz, t1z[0], t1z[1]);
-#pragma unroll
-                for (int k = 0; k < 2; k++)
-                {
-                    tn[k] = fmaxf(fmaxf(t0x[k], t0y[k]), fmaxf(t0z[k], tmin));
-                    tf[k] = fminf(fminf(t1x[k], t1y[k]), fminf(t1z[k], tmax));
-                }
-                mul_pair(tf[0], tf[1], BVH8_BOX_SLACK, tf[0], tf[1]);
-#pragma unroll
-                for (int k = 0; k < 2; k++)
-                {
-                    // branch-free: leaves contribute their unary triangle count at their triangle offset,
-                    // inner children one bit at their priority; an empty slot has meta == 0 -> 0 bits
-                    const unsigned bits = byte_of(childbits4, jp + k) << byte_of(index4, jp + k);
-                    hits |= (tn[k] <= tf[k]) ? bits : 0u;
-                }
+                const float    t0x = fmaf(float(byte_of(nearx, j)), ax, bx), t1x = fmaf(float(byte_of(farx, j)), ax, bx);
+                const float    t0y = fmaf(float(byte_of(neary, j)), ay, by), t1y = fmaf(float(byte_of(fary, j)), ay, by);
+                const float    t0z = fmaf(float(byte_of(nearz, j)), az, bz), t1z = fmaf(float(byte_of(farz, j)), az, bz);
+                const float    tn  = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+                const float    tf  = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+                // branch-free: leaves contribute their unary triangle count at their triangle offset, inner
+                // children one bit at their priority; an empty slot has meta == 0 -> 0 bits
+                const unsigned bits = byte_of(childbits4, j) << byte_of(index4, j);
+                hits |= (tn <= tf * BVH8_BOX_SLACK) ? bits : 0u;
             }
         }
         return hits;
@@ -304,7 +168,7 @@ namespace crb
             const unsigned slot       = unsigned(bit - 24) ^ octinv;
             const unsigned node_index = group.x + __popc(group.y & 0xffu & ((1u << slot) - 1u));
 
-            const uint4 *np = bvh.nodes + size_t(node_index) * BVH8_NODE_U4;
+            const uint4 *np = bvh.nodes + size_t(node_index) * 5;
             const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) ctr->nodes++;
             const unsigned h = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, best.t);
@@ -358,7 +222,6 @@ namespace crb
     {
         const unsigned FULL = 0xffffffffu;
         const unsigned lane = crb_lane_id();
-        const unsigned long long keep = l2_keep_policy();
         uint2          stack[BVH8_STACK];
         int            sp = 0;
         bool           active = false, finished = false, exhausted = false;
@@ -439,25 +302,12 @@ namespace crb
                     const unsigned slot       = unsigned(bit - 24) ^ octinv;
                     const unsigned node_index = group.x + __popc(group.y & 0xffu & ((1u << slot) - 1u));
 
-                    const uint4 *np = bvh.nodes + size_t(node_index) * BVH8_NODE_U4;
-#if !defined(CRB_EMU) && CRB_NODE256
-                    uint4 n0, n1, n2, n3, n4, npad;
-                    ld_node32(np, n0, n1), ld_node32(np + 2, n2, n3), ld_node32(np + 4, n4, npad);
-#else
-                    const uint4  n0 = ld_node16(np, keep), n1 = ld_node16(np + 1, keep), n2 = ld_node16(np + 2, keep), n3 = ld_node16(np + 3, keep),
-                                n4 = ld_node16(np + 4, keep);
-#endif
+                    const uint4 *np = bvh.nodes + size_t(node_index) * 5;
+                    const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                     if (COUNT) ctr->nodes++;
                     const unsigned h = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, best.t);
                     group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
                     tgroup           = make_uint2(n1.y, h & 0x00ffffffu);
-#if CRB_PREFETCH
-                    if (h & 0xff000000u)
-                    {
-                        const unsigned nslot = unsigned(7 - __clz(int(h & 0xff000000u))) ^ octinv;
-                        prefetch_node(bvh.nodes + size_t(n1.x + __popc((n0.w >> 24) & ((1u << nslot) - 1u))) * BVH8_NODE_U4);
-                    }
-#endif
                 }
                 // ---- leaf phase in lock step: ONE triangle per lane that has triangles waiting (an inner
                 // per-lane triangle loop was 52 % of k_trace's instructions at 2.7 active lanes; waiting for
@@ -470,7 +320,7 @@ namespace crb
                         const int i = __ffs(int(tgroup.y)) - 1;
                         tgroup.y &= tgroup.y - 1;
                         const float4 *tp = bvh.tris + size_t(tgroup.x + unsigned(i)) * 3;
-                        const float4  a = ld_tri16(tp, keep), b = ld_tri16(tp + 1, keep), c = ld_tri16(tp + 2, keep);
+                        const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
                         if (COUNT) ctr->tris++;
                         float t, u, v;
                         if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, best.t, t, u, v))

@@ -470,7 +470,7 @@ namespace crb
             }
 
             auto pack4 = [](const unsigned *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
-            uint4 *np  = c.nodes + size_t(self) * BVH8_NODE_U4;
+            uint4 *np  = c.nodes + size_t(self) * 5;
             np[0]      = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
             np[1]      = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
             np[2]      = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
@@ -509,7 +509,7 @@ namespace crb
         CRB_CUDA_CHECK(cudaEventRecord(ev0, stream));
 #endif
         const size_t max_nodes = size_t(n) / 2 + 8;
-        nodes.alloc(max_nodes * BVH8_NODE_U4);
+        nodes.alloc(max_nodes * 5);
         tris.alloc(size_t(n ? n : 1) * 3);
 
         if (n == 0)

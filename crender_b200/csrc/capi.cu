@@ -176,7 +176,7 @@ int crb_scene_commit(crb_scene *s, crb_build_info *info)
             info->upload_ms   = s->s.upload_ms;
             info->n_triangles = s->s.build.n_tris;
             info->n_nodes     = s->s.build.n_nodes;
-            info->node_bytes  = uint64_t(s->s.build.n_nodes) * 16 * crb::BVH8_NODE_U4;
+            info->node_bytes  = uint64_t(s->s.build.n_nodes) * 80;
             info->tri_bytes   = uint64_t(s->s.build.n_tris) * 48;
             info->max_depth   = s->s.build.max_depth;
             info->sah_cost    = s->s.build.sah_cost;
