@@ -165,7 +165,7 @@ def run_reference(a):
         "e2e": {"value": res["mrays"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "samples_per_s": res["samples_per_s"], "bvh_build_ms": res["build_ms"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -278,7 +278,7 @@ def run_ours(a):
         # e2e at N>1: the same step loop, wall-clocked, plus a device->host read of the merged buffer every step
         line["e2e"] = e2e_multi(a, r, step, merged, barrier, torch, dist, world)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -397,8 +397,26 @@ def e2e_multi(a, r, step, merged, barrier, torch, dist, world):
             "note": "per step: render + NCCL all-reduce of the accumulation buffers + device->host read of the merged buffer on every rank"}
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 if __name__ == "__main__":
     args = parse()
+    # libraries chat on stdout (NCCL prints its version banner there when NCCL_DEBUG=VERSION is set in the
+    # environment): keep fd 1 for the result line only, everything else goes to stderr
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
