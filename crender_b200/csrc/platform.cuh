@@ -18,6 +18,10 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
 
 #ifndef CRB_EMU
 #include <cuda_runtime.h>
@@ -231,6 +235,44 @@ __device__ __forceinline__ unsigned crb_lane_id()
 namespace crb
 {
     // ---- device memory helpers (cudaMalloc on the product; malloc in the test harness)
+#ifndef CRB_EMU
+    // Large device blocks are recycled instead of going back to the driver: cudaFree / cudaMalloc of the
+    // multi-gigabyte path state costs tens of milliseconds, and an interactive host re-creates renderers on
+    // every resolution change (renderer.cpp:194-201). Exact-size reuse per device, bounded, trimmed when an
+    // allocation fails.
+    struct DevBlockCache
+    {
+        static constexpr size_t MIN_BLOCK = size_t(1) << 20, MAX_CACHED = size_t(24) << 30;
+        std::mutex                                          mu;
+        std::multimap<std::pair<int, size_t>, void *>       free_blocks;    // (device, bytes) -> block
+        std::unordered_map<void *, std::pair<int, size_t>>  live;           // blocks handed out that are cacheable
+        size_t                                              cached = 0;
+        void trim_locked()
+        {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            for (auto &kv : free_blocks)
+            {
+                cudaSetDevice(kv.first.first);
+                cudaFree(kv.second);
+            }
+            cudaSetDevice(cur);
+            free_blocks.clear();
+            cached = 0;
+        }
+    };
+    inline DevBlockCache &dev_block_cache()
+    {
+        static DevBlockCache c;
+        return c;
+    }
+    inline size_t dev_cached_bytes()
+    {
+        DevBlockCache &c = dev_block_cache();
+        std::lock_guard<std::mutex> lk(c.mu);
+        return c.cached;
+    }
+#endif
     inline void *dev_alloc(size_t bytes)
     {
         if (bytes == 0) bytes = 16;
@@ -239,8 +281,39 @@ namespace crb
         if (!p) throw Error(ERR_OOM, "alloc failed");
         return p;
 #else
-        void *p = nullptr;
-        CRB_CUDA_CHECK(cudaMalloc(&p, bytes));
+        void          *p = nullptr;
+        DevBlockCache &c = dev_block_cache();
+        int            dev = 0;
+        CRB_CUDA_CHECK(cudaGetDevice(&dev));
+        if (bytes >= DevBlockCache::MIN_BLOCK)
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            auto                        it = c.free_blocks.find({ dev, bytes });
+            if (it != c.free_blocks.end())
+            {
+                p = it->second;
+                c.free_blocks.erase(it);
+                c.cached -= bytes;
+                c.live[p] = { dev, bytes };
+                return p;
+            }
+        }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaErrorMemoryAllocation)
+        {
+            cudaGetLastError();
+            {
+                std::lock_guard<std::mutex> lk(c.mu);
+                c.trim_locked();
+            }
+            e = cudaMalloc(&p, bytes);
+        }
+        CRB_CUDA_CHECK(e);
+        if (bytes >= DevBlockCache::MIN_BLOCK)
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            c.live[p] = { dev, bytes };
+        }
         return p;
 #endif
     }
@@ -250,6 +323,28 @@ namespace crb
 #ifdef CRB_EMU
         free(p);
 #else
+        DevBlockCache &c = dev_block_cache();
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            auto                        it = c.live.find(p);
+            if (it != c.live.end())
+            {
+                const std::pair<int, size_t> key = it->second;
+                c.live.erase(it);
+                if (c.cached + key.second <= DevBlockCache::MAX_CACHED)
+                {
+                    // same guarantee as cudaFree: nothing on the device still uses the block when it is reused
+                    int cur = 0;
+                    cudaGetDevice(&cur);
+                    if (cur != key.first) cudaSetDevice(key.first);
+                    cudaDeviceSynchronize();
+                    if (cur != key.first) cudaSetDevice(cur);
+                    c.free_blocks.insert({ key, p });
+                    c.cached += key.second;
+                    return;
+                }
+            }
+        }
         cudaFree(p);
 #endif
     }

@@ -589,9 +589,7 @@ namespace crb
     {
 #ifndef CRB_EMU
         CRB_CUDA_CHECK(cudaSetDevice(s->device));
-        cudaDeviceProp p;
-        CRB_CUDA_CHECK(cudaGetDeviceProperties(&p, s->device));
-        n_sms = p.multiProcessorCount;
+        n_sms = s->n_sms;    // (cudaGetDeviceProperties costs tens of milliseconds; the scene already asked)
         CRB_CUDA_CHECK(cudaEventCreate(&ev0));
         CRB_CUDA_CHECK(cudaEventCreate(&ev1));
 #endif
@@ -742,7 +740,7 @@ namespace crb
         {
             // never plan for more than a quarter of the free device memory (152 B of state per path)
             size_t free_b = 0, total_b = 0;
-            if (capacity == 0 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) mem_path_cap = std::max<size_t>(size_t(1) << 20, free_b / 4 / 152);
+            if (capacity == 0 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) mem_path_cap = std::max<size_t>(size_t(1) << 20, (free_b + dev_cached_bytes()) / 4 / 152);
             if (mem_path_cap) tpaths = std::min(tpaths, mem_path_cap);
         }
 #endif
