@@ -404,3 +404,26 @@ def check_trace_steps_variants_identical(lib_path):
         assert out.returncode == 0, out.stderr[-2000:]
         hashes[steps] = [ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][0]
     assert len(set(hashes.values())) == 1, hashes
+
+
+def check_recycled_memory_is_clean(lib_path):
+    """Device blocks are recycled between handles (platform.cuh DevBlockCache): a renderer that inherits the
+    path state and image buffers of a destroyed one must not see any of their contents."""
+
+    def run(desc, seed):
+        g = api.scene(lib_path=lib_path)
+        scenes.load(desc, g)
+        g.commit()
+        r = api.renderer(160, 90, 5, g, seed=seed)
+        r.render(4)
+        out = (r.raw_sum().copy(), r.current_normals().copy(), r.current_depths().copy())
+        r.close()
+        g.close()
+        return out
+
+    a0 = run(scenes.terrain_city(24, 2, n_buildings=12), 1)
+    run(scenes.textured_scene(), 2)  # same buffer sizes, different contents
+    run(scenes.cornell(), 3)
+    a1 = run(scenes.terrain_city(24, 2, n_buildings=12), 1)
+    for x, y in zip(a0, a1):
+        np.testing.assert_array_equal(x, y)

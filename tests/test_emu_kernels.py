@@ -57,3 +57,7 @@ def test_query_kinds_consistent(emu_lib):
 
 def test_instrumented_render_is_identical(emu_lib):
     pc.check_instrumented_render_is_identical(emu_lib)
+
+
+def test_recycled_memory_is_clean(emu_lib):
+    pc.check_recycled_memory_is_clean(emu_lib)

@@ -234,3 +234,7 @@ def test_instrumented_render_is_identical(product_lib):
 
 def test_trace_steps_variants_identical(product_lib):
     pc.check_trace_steps_variants_identical(product_lib)
+
+
+def test_recycled_memory_is_clean(product_lib):
+    pc.check_recycled_memory_is_clean(product_lib)
