@@ -257,11 +257,11 @@ class renderer:
     management thread issues them in a loop until the target spp, renderer.cpp:116-144)."""
 
     def __init__(self, res_x: int, res_y: int, bounces: int, scn: scene, seed: int = 0, counters: bool = False, timers: bool = False,
-                 material_sort: bool = False):
+                 material_sort: bool = False, extended: bool = False):
         self._lib = scn._lib
         self._scene = scn
         h = C.c_void_p()
-        _capi.check(self._lib, self._lib.crb_render_create(scn._h, res_x, res_y, bounces, seed, (1 if counters else 0) | (2 if timers else 0) | (4 if material_sort else 0), C.byref(h)))
+        _capi.check(self._lib, self._lib.crb_render_create(scn._h, res_x, res_y, bounces, seed, (1 if counters else 0) | (2 if timers else 0) | (4 if material_sort else 0) | (8 if extended else 0), C.byref(h)))
         self._h = h
         self._res = (res_x, res_y)
         self._spp_target = 0

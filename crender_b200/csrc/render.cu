@@ -164,7 +164,7 @@ namespace crb
             }
             ps.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.f);
             ps.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
-            ps.thr[slot]   = make_float4(1.f, 1.f, 1.f, 0.f);
+            ps.thr[slot]   = make_float4(1.f, 1.f, 1.f, 1.f);    // w: extended mode's "previous vertex was specular" flag (the camera counts)
             ps.rad[slot]   = make_float4(0.f, 0.f, 0.f, 0.f);
             ps.q_in[slot]  = slot;
             if (sample == rp.aov_sample)
@@ -433,9 +433,260 @@ namespace crb
                                 {
                                     want_shadow = true;
                                     sr.o        = make_float4(so.x, so.y, so.z, __uint_as_float(slot));
-                                    sr.d        = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                    sr.d        = make_float4(dir.x, dir.y, dir.z, inf_f());
                                     sr.c        = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
                                 }
+                            }
+                        }
+                    }
+                }
+                const bool pred[2] = { survive, want_shadow };
+                const int  cidx[2] = { CTR_NEXT, CTR_SHADOW };
+                uint32_t   at[2];
+                block_reserve<2>(pred, ps.counters, cidx, at);
+                if (survive) ps.q_next[at[0]] = slot;
+                if (want_shadow) ps.shadow[at[1]] = sr;
+            }
+        }
+
+        // ------------------------------------------------------------------ extended shading mode
+        // CRB_RENDER_FLAG_EXTENDED: GGX metal, Fresnel dielectric, Lambert with face-forwarded normals, NEE of
+        // the sun cone and of uniformly picked emissive triangles at diffuse vertices. In the reference this is
+        // dead code (cr::brdf::ggx, src/render/brdf.h:10-29; cook_torrence::*, src/util/sampling.h:83-142) and
+        // BASELINE configs 2 / 5 name it, so the mode is specified by the oracle ("EXTENDED shading mode" in
+        // oracle.cpp) and restated here operation by operation. Sampler dimensions per bounce i:
+        // 2+6i+{0,1} scatter, {2,3} light sample, {4} strategy, {5} light pick. thr.w carries the
+        // "previous vertex was specular" flag.
+        __device__ __forceinline__ float pow5(float m)
+        {
+            const float m2 = m * m;
+            return (m2 * m2) * m;
+        }
+        // src/util/sampling.h:110-118
+        __device__ __forceinline__ float specular_g(float NoV, float NoL, float a)
+        {
+            const float a2   = a * a;
+            const float ggxv = NoL * sqrtf(NoV * NoV * (1.0f - a2) + a2);
+            const float ggxl = NoV * sqrtf(NoL * NoL * (1.0f - a2) + a2);
+            return 0.5f / (ggxv + ggxl);
+        }
+        // src/util/sampling.h:21-33 (build_local), then the half vector distributed like D(h) * (n.h)
+        __device__ __forceinline__ V3 sample_ggx_h(V3 n, float a, float u0, float u1, float &cos_h)
+        {
+            const float a2    = a * a;
+            const float cos2  = (1.0f - u0) / (1.0f + (a2 - 1.0f) * u0);
+            cos_h             = sqrtf(cos2);
+            const float sin_h = sqrtf(fmaxf(0.0f, 1.0f - cos2));
+            const float phi   = TAU_F * u1;
+            const float sg    = (n.z < 0.0f) ? -1.0f : 1.0f;
+            const float ka    = -1.0f / (sg + n.z);
+            const float kb    = n.x * n.y * ka;
+            const V3    tangent = v3(1.0f + sg * n.x * n.x * ka, sg * kb, -sg * n.x), bitangent = v3(kb, sg + n.y * n.y * ka, -n.y);
+            return (tangent * (cosf(phi) * sin_h) + n * cos_h) + bitangent * (sinf(phi) * sin_h);
+        }
+
+        __global__ void __launch_bounds__(256, 3) k_shade_ext(DScene sc, RenderParams rp, PathState ps)
+        {
+            const uint32_t c0 = ps.counters[CTR_CLASS0], c1 = c0 + ps.counters[CTR_CLASS0 + 1], c2 = c1 + ps.counters[CTR_CLASS0 + 2],
+                           n = ps.sorted ? c2 + ps.counters[CTR_CLASS0 + 3] : ps.counters[CTR_IN];
+            const uint32_t i = rp.bounce, NL = sc.n_lights;
+            for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
+            {
+                const uint32_t idx     = tile + threadIdx.x;
+                bool           survive = false, want_shadow = false;
+                uint32_t       slot    = 0;
+                ShadowRay      sr;
+                if (idx < n)
+                {
+                    int cls;
+                    if (ps.sorted)
+                    {
+                        cls  = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
+                        slot = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
+                    }
+                    else
+                    {
+                        slot = ps.q_in[idx];
+                        cls  = __float_as_uint(ps.hit[slot].w) == INVALID_PRIM ? 0 : 1;
+                    }
+                    const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                    const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
+                    const float4 t4 = ps.thr[slot];
+                    const V3     thr = v3(t4.x, t4.y, t4.z);
+                    const bool   specular = t4.w != 0.0f;
+                    const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
+                    const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+                    const uint32_t sample = rp.first_sample + s;
+                    const bool     aov    = (i == 0) && (sample == rp.aov_sample);
+                    const uint32_t key    = path_key(rp.seed, x + y * rp.w, sample);
+                    const uint32_t dim    = 2 + 6 * i;
+                    const V3       dn     = normalize(d);
+
+                    if (cls == 0)
+                    {
+                        V3 ms = v3(0.f, 0.f, 0.f);
+                        if (sc.skybox)
+                        {
+                            const float mu = 0.5f + atan2f(d.z, d.x) * INV_TAU_F;
+                            const float mv = 0.5f - asinf(d.y) * INV_PI_F;
+                            const float4 c = image_get_uv(sc.skybox, sc.sky_w, sc.sky_h, mu + sc.sky_rot[0], mv + sc.sky_rot[1]);
+                            ms             = v3(c.x, c.y, c.z);
+                        }
+                        if (aov) rp.albedo[flipped_index(rp, x, y)] = make_float4(ms.x, ms.y, ms.z, 1.f);
+                        if (sc.sun.enabled && specular)
+                        {
+                            // a camera / specular path that escapes sees the sun disc (sampling.h:53-57)
+                            const float sun_angle = acosf(dot(dn, -v3(sc.sun.dir[0], sc.sun.dir[1], sc.sun.dir[2])));
+                            if (sun_angle < sc.sun.size) ms = ms + v3(sc.sun.colour[0], sc.sun.colour[1], sc.sun.colour[2]) * sc.sun.intensity;
+                            else ms = ms + v3(0.f, 0.f, 0.f);
+                        }
+                        const float4 r4 = ps.rad[slot];
+                        const V3     r  = v3(r4.x, r4.y, r4.z) + thr * ms;
+                        ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                    }
+                    else
+                    {
+                        const Surface   sf  = surface_at(sc, o, dn, ps.hit[slot]);
+                        const DMaterial mat = sc.materials[sf.mat];
+                        const float4    col = surface_colour(sc, mat, sf);
+                        if (col.w == 0.0f)
+                        {
+                            const V3 p     = sf.point + d * 0.1f;    // renderer.cpp:294-301
+                            ps.ray_o[slot] = make_float4(p.x, p.y, p.z, 0.f);
+                            survive        = true;
+                        }
+                        else
+                        {
+                            const V3   colour = v3(col.x, col.y, col.z);
+                            const bool back   = dot(d, sf.normal) > 0;
+                            const V3   ns     = back ? -sf.normal : sf.normal;
+                            if (aov)
+                            {
+                                const uint32_t fi = flipped_index(rp, x, y);
+                                rp.albedo[fi]     = make_float4(colour.x, colour.y, colour.z, 1.f);
+                                const V3 nn       = sf.normal * .5f + v3(.5f, .5f, .5f);
+                                rp.normal[fi]     = make_float4(nn.x, nn.y, nn.z, 1.f);
+                                const float dd    = fminf(sf.distance, 200.0f) / 200.f;
+                                rp.depth[fi]      = make_float4(dd, dd, dd, 1.f);
+                            }
+                            if (mat.emission > 0.0f && (specular || NL == 0))
+                            {
+                                const float4 r4 = ps.rad[slot];
+                                const V3     r  = v3(r4.x, r4.y, r4.z) + thr * (v3(mat.colour[0], mat.colour[1], mat.colour[2]) * mat.emission);
+                                ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                            }
+                            const float u0 = rnd(key, dim), u1 = rnd(key, dim + 1);
+                            V3          no, nd, weight = colour;
+                            bool        next_specular = true, absorbed = false;
+                            if (mat.shade_type == CRB_GLASS)
+                            {
+                                const float eta  = back ? mat.ior : 1.0f / mat.ior;    // renderer.cpp:52-57
+                                const float dt   = dot(dn, ns);
+                                const float disc = 1.0f - eta * eta * (1.0f - dt * dt);
+                                float       R    = 1.0f;
+                                if (disc > 0)
+                                {
+                                    const float cos_i = -dt, cos_t = sqrtf(disc);
+                                    const float rs = (eta * cos_i - cos_t) / (eta * cos_i + cos_t);
+                                    const float rp_ = (cos_i - eta * cos_t) / (cos_i + eta * cos_t);
+                                    R               = 0.5f * (rs * rs + rp_ * rp_);
+                                }
+                                if (u0 < R)
+                                {
+                                    no = sf.point + ns * 0.0001f;
+                                    nd = reflect(dn, ns);
+                                }
+                                else
+                                {
+                                    no = sf.point + ns * -0.0001f;
+                                    nd = eta * (dn - ns * dt) - ns * sqrtf(disc);    // renderer.cpp:63-67
+                                }
+                            }
+                            else if (mat.shade_type == CRB_METAL)
+                            {
+                                const float a = clampf(mat.roughness, 0.02f, 1.0f);
+                                float       NoH;
+                                const V3    h   = sample_ggx_h(ns, a, u0, u1, NoH);
+                                const V3    wi  = reflect(dn, h);
+                                const float VoH = -dot(dn, h), NoL = dot(ns, wi), NoV = -dot(dn, ns);
+                                if (!(VoH > 0 && NoL > 0 && NoV > 0))
+                                    absorbed = true;
+                                else
+                                {
+                                    const V3    f0 = colour * mat.reflectiveness;
+                                    const float f  = pow5(1.0f - VoH);
+                                    const V3    F  = v3(f + f0.x * (1.0f - f), f + f0.y * (1.0f - f), f + f0.z * (1.0f - f));    // sampling.h:137-141
+                                    const float g  = specular_g(NoV, NoL, a) * 4.0f * VoH * NoL / NoH;
+                                    weight         = F * g;
+                                    no             = sf.point + ns * 0.0001f;
+                                    nd             = wi;
+                                }
+                            }
+                            else
+                            {
+                                no            = sf.point + ns * 0.0001f;
+                                nd            = normalize(ns + sample_sphere(u0, u1));
+                                next_specular = false;
+                            }
+
+                            // next-event estimation at diffuse vertices: the sun cone or one emissive triangle
+                            if (!next_specular && (sc.sun.enabled || NL))
+                            {
+                                const V3    so   = sf.point + ns * 0.001f;
+                                const V3    bsdf = (thr * colour) * INV_PI_F;
+                                const bool  both = sc.sun.enabled && NL;
+                                const bool  use_sun = sc.sun.enabled && (!NL || rnd(key, dim + 4) < 0.5f);
+                                const float u2 = rnd(key, dim + 2), u3 = rnd(key, dim + 3);
+                                V3          contrib = v3(0.f, 0.f, 0.f), dir = v3(0.f, 1.f, 0.f);
+                                float       tmax = inf_f();
+                                if (use_sun)
+                                {
+                                    const V3     l = map_to_solid_angle(u2, u3, sc.sun.one_minus_cos);
+                                    const float *T = sc.sun.transform;
+                                    dir            = (v3(T[0], T[1], T[2]) * l.x + v3(T[3], T[4], T[5]) * l.y) + v3(T[6], T[7], T[8]) * l.z;
+                                    const float cosine    = clampf(dot(ns, dir), 0.0f, 1.0f);
+                                    const float sun_angle = acosf(dot(dir, -v3(sc.sun.dir[0], sc.sun.dir[1], sc.sun.dir[2])));
+                                    const V3    sky = (sun_angle < sc.sun.size) ? v3(sc.sun.colour[0], sc.sun.colour[1], sc.sun.colour[2]) * sc.sun.intensity
+                                                                                : v3(0.f, 0.f, 0.f);
+                                    contrib         = bsdf * cosine * sky / sc.sun.pdf;
+                                }
+                                else
+                                {
+                                    uint32_t k = uint32_t(rnd(key, dim + 5) * float(NL));
+                                    if (k >= NL) k = NL - 1;
+                                    const float4 l0 = __ldg(sc.lights + 3 * size_t(k)), l1 = __ldg(sc.lights + 3 * size_t(k) + 1), l2 = __ldg(sc.lights + 3 * size_t(k) + 2);
+                                    const V3     v0 = v3(l0.x, l0.y, l0.z), e1 = v3(l1.x, l1.y, l1.z), e2 = v3(l2.x, l2.y, l2.z), le = v3(l0.w, l1.w, l2.w);
+                                    float        b1 = u2, b2 = u3;
+                                    if (b1 + b2 > 1.0f) b1 = 1.0f - b1, b2 = 1.0f - b2;
+                                    const V3    q  = (v0 + e1 * b1) + e2 * b2;
+                                    const V3    wv = q - so;
+                                    const float d2 = dot(wv, wv);
+                                    if (d2 > 0.0f)
+                                    {
+                                        const float dist  = sqrtf(d2);
+                                        dir               = wv * (1.0f / dist);
+                                        const float cos_s = clampf(dot(ns, dir), 0.0f, 1.0f);
+                                        const float g     = cos_s * (0.5f * fabsf(dot(cross(e1, e2), dir))) / d2 * float(NL);
+                                        contrib           = bsdf * le * g;
+                                        tmax              = dist * 0.999f;
+                                    }
+                                }
+                                if (both) contrib = contrib * 2.0f;
+                                if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f)
+                                {
+                                    want_shadow = true;
+                                    sr.o        = make_float4(so.x, so.y, so.z, __uint_as_float(slot));
+                                    sr.d        = make_float4(dir.x, dir.y, dir.z, tmax);
+                                    sr.c        = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                                }
+                            }
+                            if (!absorbed)
+                            {
+                                const V3 t  = thr * weight;
+                                ps.thr[slot]   = make_float4(t.x, t.y, t.z, next_specular ? 1.f : 0.f);
+                                ps.ray_o[slot] = make_float4(no.x, no.y, no.z, 0.f);
+                                ps.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, 0.f);
+                                survive        = true;
                             }
                         }
                     }
@@ -461,7 +712,7 @@ namespace crb
                 const float4 so = ps.shadow[idx].o, sd = ps.shadow[idx].d;
                 o               = v3(so.x, so.y, so.z);
                 d               = normalize(v3(sd.x, sd.y, sd.z));    // model.cpp:110-112
-                tmin = 0.00001f, tmax = inf_f();
+                tmin = 0.00001f, tmax = sd.w;                         // inf for the sun, 0.999 * distance for an area light
             };
             auto sink = [&](bool valid, uint32_t item, const Hit &h) {
                 if (valid && h.prim == INVALID_PRIM)
@@ -500,6 +751,7 @@ namespace crb
                     const V3        d  = v3(sr.d.x, sr.d.y, sr.d.z);
                     const V3        dn = normalize(d);    // model.cpp:110-112
                     bool            visible = false;
+                    float           remaining = sr.d.w;    // inf for the sun (the reference's loop), finite for area lights (extended mode)
                     for (int guard = 0; guard < 4096; guard++)
                     {
                         const Hit h = traverse<false, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), &tc);
@@ -509,9 +761,16 @@ namespace crb
                             break;
                         }
                         const Surface   sf  = surface_at(sc, o, dn, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
+                        if (!(sf.distance <= remaining))
+                        {
+                            visible = true;
+                            break;
+                        }
                         const DMaterial mat = sc.materials[sf.mat];
                         if (surface_colour(sc, mat, sf).w != 0.0f) break;
-                        o = sf.point + d * 0.1f;    // marches in 0.1 steps of the un-normalised direction
+                        const V3 next = sf.point + d * 0.1f;    // marches in 0.1 steps of the un-normalised direction
+                        remaining     = remaining - length(next - o);
+                        o             = next;
                     }
                     if (visible)
                     {
@@ -809,10 +1068,13 @@ namespace crb
                 tock();
                 tick(CRB_K_SHADE);
                 if (ps.sorted) CRB_LAUNCH(k_classify, pgrid, pblock, st, dscene, ps);
-                CRB_LAUNCH(k_shade, pgrid, pblock, st, dscene, rp, ps);
+                if (flags & CRB_RENDER_FLAG_EXTENDED)
+                    CRB_LAUNCH(k_shade_ext, pgrid, pblock, st, dscene, rp, ps);
+                else
+                    CRB_LAUNCH(k_shade, pgrid, pblock, st, dscene, rp, ps);
                 tock();
                 launches += ps.sorted ? 3 : 2;
-                if (dscene.sun.enabled)
+                if (dscene.sun.enabled || ((flags & CRB_RENDER_FLAG_EXTENDED) && dscene.n_lights))
                 {
                     tick(CRB_K_SHADOW);
                     if (dscene.has_alpha)

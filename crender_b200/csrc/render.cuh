@@ -8,8 +8,8 @@ namespace crb
     struct ShadowRay    // 48 bytes
     {
         float4 o;    // xyz origin, w = path slot (bits)
-        float4 d;    // xyz direction as sampled (un-normalised), w unused
-        float4 c;    // rgb contribution added to the path if the sun is visible
+        float4 d;    // xyz direction as sampled (un-normalised), w = tmax (inf for the sun)
+        float4 c;    // rgb contribution added to the path if the light is visible
     };
 
     // device pointers of the path-state SoA, indexed by path slot = sample_in_batch * npix + pixel
@@ -17,7 +17,7 @@ namespace crb
     {
         float4 *ray_o;    // xyz origin
         float4 *ray_d;    // xyz direction exactly as the reference's cr::ray::direction (not re-normalised)
-        float4 *thr;      // xyz throughput
+        float4 *thr;      // xyz throughput, w = extended mode: previous vertex was specular
         float4 *rad;      // xyz radiance ("final")
         float4 *hit;      // t (normalised-direction units), u, v, flat prim (bits)
         uint32_t *q_in;         // active path slots of this bounce

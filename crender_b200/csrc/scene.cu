@@ -183,7 +183,7 @@ namespace crb
                 DMaterial d {};
                 memcpy(d.colour, s.colour, 16);
                 d.shade_type = s.shade_type > 2 ? uint32_t(CRB_SMOOTH) : s.shade_type;
-                d.ior = s.ior, d.reflectiveness = s.reflectiveness, d.emission = s.emission, d.tex = s.tex;
+                d.ior = s.ior, d.reflectiveness = s.reflectiveness, d.emission = s.emission, d.tex = s.tex, d.roughness = s.roughness;
                 dm.push_back(d);
                 if (s.tex >= 0)
                 {
@@ -200,6 +200,37 @@ namespace crb
             }
         d_materials.alloc(dm.size() ? dm.size() : 1);
         dev_upload(d_materials.p, dm.data(), dm.size() * sizeof(DMaterial), stream);
+
+        // light list of the extended shading mode: every emissive, non-cut-out triangle in world space, in
+        // (model, instance, triangle) order; same arithmetic as k_flatten
+        std::vector<float4> lt;
+        for (const HostModel &m : models)
+        {
+            bool any = false;
+            for (const crb_material &s : m.materials) any = any || (s.emission > 0.0f && s.colour[3] != 0.0f);
+            if (!any) continue;
+            for (size_t ii = 0; ii < m.transforms.size() / 16; ii++)
+            {
+                const float *M = &m.transforms[16 * ii];
+                for (uint32_t t = 0; t < m.ntris; t++)
+                {
+                    const crb_material &s = m.materials[m.mat_idx[t]];
+                    if (!(s.emission > 0.0f) || s.colour[3] == 0.0f) continue;
+                    float w[9];
+                    for (int k = 0; k < 3; k++)
+                    {
+                        const float x = m.verts[size_t(t) * 9 + 3 * k], y = m.verts[size_t(t) * 9 + 3 * k + 1], z = m.verts[size_t(t) * 9 + 3 * k + 2];
+                        for (int r = 0; r < 3; r++) w[3 * k + r] = (M[0 + r] * x + M[4 + r] * y) + (M[8 + r] * z + M[12 + r]);
+                    }
+                    lt.push_back(make_float4(w[0], w[1], w[2], s.colour[0] * s.emission));
+                    lt.push_back(make_float4(w[3] - w[0], w[4] - w[1], w[5] - w[2], s.colour[1] * s.emission));
+                    lt.push_back(make_float4(w[6] - w[0], w[7] - w[1], w[8] - w[2], s.colour[2] * s.emission));
+                }
+            }
+        }
+        n_lights = uint32_t(lt.size() / 3);
+        d_lights.alloc(lt.size() ? lt.size() : 1);
+        dev_upload(d_lights.p, lt.data(), lt.size() * sizeof(float4), stream);
         stream_sync(stream);
     }
 
@@ -331,6 +362,7 @@ namespace crb
         d.sky_rot[0] = sky_rot[0], d.sky_rot[1] = sky_rot[1];
         d.ranges = d_ranges.p, d.n_ranges = uint32_t(ranges.size());
         d.has_alpha = has_alpha ? 1u : 0u;
+        d.lights = d_lights.p, d.n_lights = n_lights;
 
         // ---- sun: registry.cpp:248-256 + sampling.h:21-47 (host libm, same as the reference's CPU)
         DSun &s = d.sun;

@@ -22,7 +22,8 @@ namespace crb
         uint32_t shade_type;
         float    ior, reflectiveness, emission;
         int32_t  tex;
-        uint32_t pad[3];
+        float    roughness;    // extended shading mode only (dead in the reference, renderer.cpp:84-86)
+        uint32_t pad[2];
     };
 
     struct DTexture
@@ -75,6 +76,8 @@ namespace crb
         const FlatRange *ranges;
         uint32_t        n_ranges;
         uint32_t        has_alpha;    // any material that can produce colour.w == 0
+        const float4   *lights;       // extended mode: 3 per emissive world-space triangle: (v0, Le.r) (e1, Le.g) (e2, Le.b)
+        uint32_t        n_lights;
         DSun            sun;
         DCamera         cam;
     };
@@ -120,6 +123,8 @@ namespace crb
         DBuf<float4>     d_texels;
         DBuf<float4>     d_skybox;
         DBuf<FlatRange>  d_ranges;
+        DBuf<float4>     d_lights;         // emissive triangles for the extended mode's area-light NEE
+        uint32_t         n_lights = 0;
         DBuf<uint4>      d_nodes;
         DBuf<float4>     d_tris;
         std::vector<FlatRange> ranges;
@@ -136,7 +141,7 @@ namespace crb
         void set_instances(int model, const float *mats, uint32_t n);
         int  add_texture(const float *rgba, uint32_t w, uint32_t h);
         void commit();
-        void upload_materials();    // also recomputes has_alpha
+        void upload_materials();    // also recomputes has_alpha and the light list
         void upload_skybox();
         DScene device_scene(uint32_t w, uint32_t h) const;    // camera aspect from the render target
         void   require_committed() const;

@@ -50,7 +50,7 @@ typedef struct crb_material
 {
     uint32_t shade_type;     /* default CRB_SMOOTH */
     float    ior;            /* 1.5 */
-    float    roughness;      /* 0.5 (dead in the reference: renderer.cpp:84-86 is commented out) */
+    float    roughness;      /* 0.5 (dead in the reference: renderer.cpp:84-86 is commented out; GGX alpha in extended mode) */
     float    reflectiveness; /* 1 */
     float    emission;       /* 0 */
     float    colour[4];      /* 1,1,1,1; colour[3]==0 is an alpha cut-out (renderer.cpp:37-41) */
@@ -186,7 +186,10 @@ int crb_last_query_ms(crb_scene *, double *ms);
 
 /* ---- renderer: cr::renderer (src/render/renderer.h:24-105) */
 /* CRB_RENDER_FLAG_MATERIAL_SORT: sort the traced paths by shade class (miss/metal/smooth/glass) before shading */
-enum { CRB_RENDER_FLAG_COUNTERS = 1, CRB_RENDER_FLAG_TIMERS = 2, CRB_RENDER_FLAG_MATERIAL_SORT = 4 };
+/* CRB_RENDER_FLAG_EXTENDED: the shading BASELINE configs 2 and 5 name — Lambert / GGX metal (crb_material.roughness)
+ * / Fresnel dielectric, NEE of the sun and of emissive triangles at diffuse vertices. Dead code in the reference
+ * (src/render/brdf.h:10-29, src/util/sampling.h:83-142), specified by the oracle's extended mode. */
+enum { CRB_RENDER_FLAG_COUNTERS = 1, CRB_RENDER_FLAG_TIMERS = 2, CRB_RENDER_FLAG_MATERIAL_SORT = 4, CRB_RENDER_FLAG_EXTENDED = 8 };
 /* renderer::renderer(res_x,res_y,bounces,pool,scene) (renderer.cpp:106-145) + set_resolution's aspect
  * (renderer.cpp:194-208). seed keys the counter-based sampler (DESIGN.md "Sampler"). */
 int crb_render_create(crb_scene *, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags, crb_render **out);

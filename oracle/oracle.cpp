@@ -747,6 +747,132 @@ namespace
         return (sun_angle < sun.size) ? V3(sun.colour[0], sun.colour[1], sun.colour[2]) * sun.intensity : V3(0, 0, 0);
     }
 
+    // ================================================================ EXTENDED shading mode
+    // north_star / BASELINE configs 2 and 5 name "Lambert / GGX metal / Fresnel dielectric with NEE shadow
+    // rays" and "64 area lights with NEE". In the reference those are DEAD code (SURVEY.md D5:
+    // cr::brdf::ggx, src/render/brdf.h:10-29, and cook_torrence::*, src/util/sampling.h:83-142, are never
+    // called; there is no area-light NEE). The extended mode is therefore SPECIFIED HERE, by the oracle
+    // ("parity unpinned" by the reference; the product is checked against this restatement only). It keeps
+    // everything of the ref-exact path (camera, sampler, cast_ray, alpha skip, AOVs, accumulation) and
+    // replaces process_hit + NEE by:
+    //   * shading normal ns = geometric normal flipped against the ray (the reference never face-forwards);
+    //   * smooth: Lambert, wi = normalize(ns + sphere(u0,u1)) (sampling.h:156-172), weight = colour;
+    //   * metal:  GGX microfacet reflection with the reference's own G term (sampling.h:110-118; D of :94-100 cancels against the sampling pdf; a =
+    //             clamp(roughness, 0.02, 1)), Schlick Fresnel with f0 = colour * reflectiveness
+    //             (sampling.h:137-141 per channel); half vector sampled from D*cos, weight = F*Vis*4*VoH*NoL/NoH;
+    //   * glass:  exact unpolarised Fresnel reflectance R on top of the reference's refraction arithmetic
+    //             (renderer.cpp:47-77); reflect with probability R (u0 < R), else refract; weight = colour;
+    //   * emission: Le = material colour * emission, added on a hit only if the previous vertex was
+    //             specular / the camera, or if the scene has no light list (no double counting with NEE);
+    //   * NEE at smooth hits only: the sun cone (sampling.h:35-57,72-80) and/or ONE uniformly picked emissive
+    //             triangle (uniform point, two-sided emitter); when both exist one of the two strategies is
+    //             picked with probability 1/2. BSDF = colour/pi. Shadow ray from p + ns*1e-3, any hit in
+    //             (1e-5, tmax], tmax = 0.999*distance for area lights, inf for the sun; alpha cut-outs are
+    //             marched through in 0.1 steps like the reference's shadow loop (renderer.cpp:335-345);
+    //   * a specular or camera path that escapes also sees the sun disc (sky_colour, sampling.h:53-57).
+    // Sampler dimensions per bounce i: 2+6i+{0,1} scatter, {2,3} light sample, {4} strategy, {5} light pick.
+    struct area_light
+    {
+        vec3 v0, e1, e2, le;
+    };
+
+    inline float pow5(float m)
+    {
+        const float m2 = m * m;
+        return (m2 * m2) * m;
+    }
+    // sampling.h:110-118
+    inline float specular_g(float NoV, float NoL, float a)
+    {
+        const float a2   = a * a;
+        const float ggxv = NoL * std::sqrt(NoV * NoV * (1.0f - a2) + a2);
+        const float ggxl = NoV * std::sqrt(NoL * NoL * (1.0f - a2) + a2);
+        return 0.5f / (ggxv + ggxl);
+    }
+    // half vector distributed like D(h) * (n.h), in the frame of build_local (y = normal)
+    inline vec3 sample_ggx_h(vec3 ns, float a, float u0, float u1, float &cos_h)
+    {
+        const float a2   = a * a;
+        const float cos2 = (1.0f - u0) / (1.0f + (a2 - 1.0f) * u0);
+        cos_h            = std::sqrt(cos2);
+        const float sin_h = std::sqrt(std::max(0.0f, 1.0f - cos2));
+        const float phi   = TAU * u1;
+        const local_coords lc = build_local(ns);
+        return (lc.tangent * (std::cos(phi) * sin_h) + lc.normal * cos_h) + lc.bi_tangent * (std::sin(phi) * sin_h);
+    }
+    struct ext_scatter
+    {
+        bool absorbed = false, specular = false;
+        vec3 weight;
+        ray  r;
+    };
+    ext_scatter scatter_extended(const orc_material &mat, vec3 colour, vec3 n, vec3 point, const ray &r, float u0, float u1)
+    {
+        ext_scatter out;
+        const vec3  dn = normalize(r.direction);
+        const vec3  ns = (dot(r.direction, n) > 0) ? -n : n;
+        switch (mat.shade_type)
+        {
+        case ORC_GLASS:
+        {
+            const float eta  = (dot(r.direction, n) > 0) ? mat.ior : 1.0f / mat.ior;    // renderer.cpp:52-57
+            const float dt   = dot(dn, ns);
+            const float disc = 1.0f - eta * eta * (1 - dt * dt);
+            float       R    = 1.0f;
+            if (disc > 0)
+            {
+                const float cos_i = -dt, cos_t = std::sqrt(disc);
+                const float rs = (eta * cos_i - cos_t) / (eta * cos_i + cos_t);
+                const float rp = (cos_i - eta * cos_t) / (cos_i + eta * cos_t);
+                R              = 0.5f * (rs * rs + rp * rp);
+            }
+            if (u0 < R)
+            {
+                out.r.origin    = point + ns * 0.0001f;
+                out.r.direction = reflect(dn, ns);
+            }
+            else
+            {
+                out.r.origin    = point + ns * -0.0001f;
+                out.r.direction = eta * (dn - ns * dt) - ns * std::sqrt(disc);    // renderer.cpp:63-67
+            }
+            out.weight   = colour;
+            out.specular = true;
+            break;
+        }
+        case ORC_METAL:
+        {
+            const float a = clampf(mat.roughness, 0.02f, 1.0f);
+            float       NoH;
+            const vec3  h   = sample_ggx_h(ns, a, u0, u1, NoH);
+            const vec3  wi  = reflect(dn, h);
+            const float VoH = -dot(dn, h), NoL = dot(ns, wi), NoV = -dot(dn, ns);
+            out.specular    = true;
+            if (!(VoH > 0 && NoL > 0 && NoV > 0))
+            {
+                out.absorbed = true;
+                break;
+            }
+            const vec3  f0 = colour * mat.reflectiveness;
+            const float f  = pow5(1.0f - VoH);
+            const vec3  F  = V3(f + f0.x * (1.0f - f), f + f0.y * (1.0f - f), f + f0.z * (1.0f - f));    // sampling.h:137-141
+            const float g  = specular_g(NoV, NoL, a) * 4.0f * VoH * NoL / NoH;
+            out.weight      = F * g;
+            out.r.origin    = point + ns * 0.0001f;
+            out.r.direction = wi;
+            break;
+        }
+        default:
+        {
+            out.r.origin    = point + ns * 0.0001f;
+            out.r.direction = normalize(hemp_cos(ns, u0, u1));
+            out.weight      = colour;
+            break;
+        }
+        }
+        return out;
+    }
+
     struct render
     {
         scene             *sc;
@@ -757,6 +883,9 @@ namespace
         std::vector<float> buffer, normals, albedo, depth;     // renderer.h:87-91 RGBA f32
         uint32_t           current_sample = 0;
         std::atomic<uint64_t> total_queries { 0 }, ref_rays { 0 }, pixel_samples { 0 };
+        bool                    extended = false;    // see "EXTENDED shading mode" above
+        bool                    light_nee = true;    // false: leave the light list empty (emitters found by hits only; estimator cross-check)
+        std::vector<area_light> lights;              // emissive triangles in world space, (model, instance, triangle) order
 
         render(scene *s, uint32_t w_, uint32_t h_, uint32_t mb, uint32_t seed_) : sc(s), w(w_), h(h_), max_bounces(mb), seed(seed_)
         {
@@ -853,7 +982,11 @@ namespace
                 }
             }
             fired += uint64_t(total_bounces);
+            write_pixel(x, y, final, albedo_, normal_, depth_);
+        }
 
+        void write_pixel(uint64_t x, uint64_t y, vec3 final, vec3 albedo_, vec3 normal_, float depth_)
+        {
             // flip, renderer.cpp:358-365
             y = h - 1 - y;
             x = w - 1 - x;
@@ -872,11 +1005,138 @@ namespace
                       std::pow(clampf(raw[base + 2] / n, 0.0f, 1.0f), 1.f / 2.2f)));
         }
 
+        void build_lights()
+        {
+            lights.clear();
+            if (!light_nee) return;
+            for (const model &m : sc->models)
+                for (const mat4 &T : m.transforms)
+                    for (uint32_t t = 0; t < m.ntris; t++)
+                    {
+                        const orc_material &mat = m.materials[m.mat_idx[t]];
+                        if (!(mat.emission > 0.0f) || mat.colour[3] == 0.0f) continue;
+                        const vec3 v0 = mul_point(T, m.verts[3 * t]), v1 = mul_point(T, m.verts[3 * t + 1]), v2 = mul_point(T, m.verts[3 * t + 2]);
+                        lights.push_back(area_light { v0, v1 - v0, v2 - v0, V3(mat.colour[0], mat.colour[1], mat.colour[2]) * mat.emission });
+                    }
+        }
+
+        // any non-alpha hit in (1e-5, tmax] along a unit direction; alpha cut-outs are stepped through
+        bool visible_ext(vec3 o, vec3 dir, float tmax, uint64_t &queries)
+        {
+            ray   sr { o, dir };
+            float remaining = tmax;
+            for (int guard = 0; guard < 4096; guard++)
+            {
+                const record h = sc->cast_ray(sr);
+                queries++;
+                if (h.distance == INF || !(h.distance <= remaining)) return true;
+                const orc_material &mat = *h.material;
+                const float alpha = (mat.tex >= 0) ? sc->textures[size_t(mat.tex)].get_uv(h.uv.x, h.uv.y).w : mat.colour[3];
+                if (alpha != 0.0f) return false;
+                const vec3 next = h.point + dir * 0.1f;
+                remaining       = remaining - length(next - sr.origin);
+                sr.origin       = next;
+            }
+            return false;
+        }
+
+        // the extended-mode path loop (same skeleton as renderer.cpp:258-384)
+        void sample_pixel_ext(uint64_t x, uint64_t y, uint32_t sample, uint64_t &queries, uint64_t &fired)
+        {
+            const uint32_t key = path_key(seed, uint32_t(x + y * w), sample);
+            ray r = sc->cam.get_ray((float(x) + rnd(key, 0)) / float(uint64_t(w)), (float(y) + rnd(key, 1)) / float(uint64_t(h)), aspect);
+
+            vec3  throughput = V3(1, 1, 1), final = V3(0, 0, 0), albedo_ = V3(0, 0, 0), normal_ = V3(0, 0, 0);
+            float depth_     = 0.0f;
+            bool  specular   = true;    // the camera counts as a specular vertex
+            const uint32_t NL = uint32_t(lights.size());
+
+            int total_bounces = 1;
+            for (uint32_t i = 0; i < max_bounces; i++, total_bounces++)
+            {
+                const uint32_t dim   = 2 + 6 * i;
+                record         isect = sc->cast_ray(r);
+                queries++;
+                if (isect.distance == INF)
+                {
+                    const float mu = 0.5f + std::atan2(r.direction.z, r.direction.x) * INV_TAU;
+                    const float mv = 0.5f - std::asin(r.direction.y) * INV_PI;
+                    vec3        ms = sc->sample_skybox(mu, mv);
+                    if (i == 0) albedo_ = ms;
+                    if (sc->sun_enabled && specular) ms = ms + sky_colour(normalize(r.direction), sc->sun);
+                    final = final + throughput * ms;
+                    break;
+                }
+                const orc_material &mat = *isect.material;
+                vec4                col = vec4 { mat.colour[0], mat.colour[1], mat.colour[2], mat.colour[3] };
+                if (mat.tex >= 0) col = sc->textures[size_t(mat.tex)].get_uv(isect.uv.x, isect.uv.y);
+                if (col.w == 0.0)
+                {
+                    r.origin = isect.point + r.direction * 0.1f;    // renderer.cpp:294-301
+                    continue;
+                }
+                const vec3 colour = V3(col.x, col.y, col.z);
+                if (i == 0) albedo_ = colour, normal_ = isect.normal, depth_ = isect.distance;
+                if (mat.emission > 0.0f && (specular || NL == 0))
+                    final = final + throughput * (V3(mat.colour[0], mat.colour[1], mat.colour[2]) * mat.emission);
+
+                const ext_scatter sc_out = scatter_extended(mat, colour, isect.normal, isect.point, r, rnd(key, dim), rnd(key, dim + 1));
+                const vec3        ns     = (dot(r.direction, isect.normal) > 0) ? -isect.normal : isect.normal;
+
+                // next-event estimation at diffuse vertices
+                if (!sc_out.specular && (sc->sun_enabled || NL))
+                {
+                    const vec3  so   = isect.point + ns * 0.001f;
+                    const vec3  bsdf = (throughput * colour) * INV_PI;
+                    const bool  both = sc->sun_enabled && NL;
+                    const bool  use_sun = sc->sun_enabled && (!NL || rnd(key, dim + 4) < 0.5f);
+                    const float u2 = rnd(key, dim + 2), u3 = rnd(key, dim + 3);
+                    vec3        contrib = V3(0, 0, 0), dir = V3(0, 1, 0);
+                    float       tmax = INF;
+                    if (use_sun)
+                    {
+                        dir                = mul(sc->sun_transform, map_to_solid_angle(u2, u3, sc->sun.size));
+                        const float cosine = clampf(dot(ns, dir), 0.0f, 1.0f);
+                        contrib            = bsdf * cosine * sky_colour(dir, sc->sun) / solid_angle_mapping_pdf(sc->sun.size);
+                    }
+                    else
+                    {
+                        uint32_t k = uint32_t(rnd(key, dim + 5) * float(NL));
+                        if (k >= NL) k = NL - 1;
+                        const area_light &L = lights[k];
+                        float             b1 = u2, b2 = u3;
+                        if (b1 + b2 > 1.0f) b1 = 1.0f - b1, b2 = 1.0f - b2;
+                        const vec3  q  = (L.v0 + L.e1 * b1) + L.e2 * b2;
+                        const vec3  wv = q - so;
+                        const float d2 = dot(wv, wv);
+                        if (d2 > 0.0f)
+                        {
+                            const float dist  = std::sqrt(d2);
+                            dir               = wv * (1.0f / dist);
+                            const float cos_s = clampf(dot(ns, dir), 0.0f, 1.0f);
+                            const float g     = cos_s * (0.5f * std::fabs(dot(cross(L.e1, L.e2), dir))) / d2 * float(NL);
+                            contrib           = bsdf * L.le * g;
+                            tmax              = dist * 0.999f;
+                        }
+                    }
+                    if (both) contrib = contrib * 2.0f;
+                    if ((contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f) && visible_ext(so, dir, tmax, queries)) final = final + contrib;
+                }
+                if (sc_out.absorbed) break;
+                throughput = throughput * sc_out.weight;
+                r          = sc_out.r;
+                specular   = sc_out.specular;
+            }
+            fired += uint64_t(total_bounces);
+            write_pixel(x, y, final, albedo_, normal_, depth_);
+        }
+
         // renderer.cpp:116-144, 240-256 + thread_pool.cpp:40-60: one task per scanline per pass,
         // the pass is a barrier.
         void run(uint32_t first_sample, uint32_t n, int nthreads)
         {
             if (nthreads < 1) nthreads = 1;
+            if (extended) build_lights();
             for (uint32_t s = 0; s < n; s++)
             {
                 const uint32_t        sample = first_sample + s;
@@ -887,7 +1147,11 @@ namespace
                         const uint32_t y = next_row.fetch_add(1);
                         if (y >= row1) break;
                         uint64_t q = 0, fired = 0;
-                        for (uint32_t x = 0; x < w; x++) sample_pixel(x, y, sample, q, fired, nullptr);
+                        for (uint32_t x = 0; x < w; x++)
+                            if (extended)
+                                sample_pixel_ext(x, y, sample, q, fired);
+                            else
+                                sample_pixel(x, y, sample, q, fired, nullptr);
                         total_queries += q;
                         ref_rays += fired;
                         pixel_samples += w;
@@ -1077,6 +1341,7 @@ void orc_occluded_batch(orc_scene *s, const orc_ray *rays, uint8_t *occ, uint64_
 orc_render *orc_render_create(orc_scene *s, uint32_t w, uint32_t h, uint32_t mb, uint32_t seed) { return new orc_render(&s->s, w, h, mb, seed); }
 void        orc_render_destroy(orc_render *r) { delete r; }
 void        orc_render_reset(orc_render *r) { r->r.reset(); }
+void        orc_render_set_extended(orc_render *r, int on) { r->r.extended = on != 0, r->r.light_nee = on != 2; }
 void        orc_render_set_rows(orc_render *r, uint32_t y0, uint32_t y1) { r->r.row0 = y0, r->r.row1 = std::min(y1, r->r.h); }
 void        orc_render_samples(orc_render *r, uint32_t first, uint32_t n, int nthreads) { r->r.run(first, n, nthreads); }
 
@@ -1167,6 +1432,15 @@ void orc_kat_process_hit(const orc_material *m, const float *n3, const float *p3
     d_out[0] = ph.r.direction.x, d_out[1] = ph.r.direction.y, d_out[2] = ph.r.direction.z;
     albedo3[0] = ph.albedo.x, albedo3[1] = ph.albedo.y, albedo3[2] = ph.albedo.z;
     *is_alpha  = ph.is_alpha;
+}
+int orc_kat_scatter_extended(const orc_material *m, const float *n3, const float *p3, const float *d3, float u0, float u1, float *w3, float *o3, float *dir3)
+{
+    const ray         r { V3(0, 0, 0), V3(d3[0], d3[1], d3[2]) };
+    const ext_scatter e = scatter_extended(*m, V3(m->colour[0], m->colour[1], m->colour[2]), V3(n3[0], n3[1], n3[2]), V3(p3[0], p3[1], p3[2]), r, u0, u1);
+    w3[0] = e.weight.x, w3[1] = e.weight.y, w3[2] = e.weight.z;
+    o3[0] = e.r.origin.x, o3[1] = e.r.origin.y, o3[2] = e.r.origin.z;
+    dir3[0] = e.r.direction.x, dir3[1] = e.r.direction.y, dir3[2] = e.r.direction.z;
+    return e.absorbed ? 2 : (e.specular ? 1 : 0);
 }
 float orc_kat_resolve(float sum, uint32_t n_plus_1) { return std::pow(clampf(sum / float(n_plus_1), 0.0f, 1.0f), 1.f / 2.2f); }
 int   orc_kat_tri(const float *a, const float *b, const float *c, const float *o, const float *d, float tmin, float tmax, float *t, float *u, float *v)

@@ -103,6 +103,10 @@ void orc_occluded_batch(orc_scene *, const orc_ray *rays, uint8_t *occluded, uin
 orc_render *orc_render_create(orc_scene *, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed);
 void        orc_render_destroy(orc_render *);
 void        orc_render_reset(orc_render *);
+/* extended shading mode (GGX metal, Fresnel dielectric, area-light + sun NEE at diffuse vertices): specified
+ * by the oracle itself, see "EXTENDED shading mode" in oracle.cpp — the reference has only dead code for it.
+ * on = 2: extended without the light list (emitters are found by path hits only), used to cross-check the NEE estimator */
+void        orc_render_set_extended(orc_render *, int on);
 /* rows [y0,y1) only (bounded CPU samples for benchmarks); full frame = 0,h */
 void orc_render_set_rows(orc_render *, uint32_t y0, uint32_t y1);
 /* renders passes first_sample .. first_sample+n-1, one task per scanline per pass (renderer.cpp:240-256) */
@@ -127,6 +131,10 @@ void  orc_kat_sphere(float u, float v, float *out3);
 void  orc_kat_process_hit(const orc_material *, const float *normal3, const float *point3,
                           const float *raydir3, float u0, float u1, float *origin3, float *dir3,
                           float *albedo3, int *is_alpha);
+/* extended-mode scatter on a synthetic record: out weight3, origin3, dir3; returns 0 scattered diffuse,
+ * 1 scattered specular, 2 absorbed */
+int   orc_kat_scatter_extended(const orc_material *, const float *normal3, const float *point3, const float *raydir3, float u0, float u1,
+                               float *weight3, float *origin3, float *dir3);
 float orc_kat_resolve(float sum, uint32_t n_plus_1);
 int   orc_kat_tri(const float *v0, const float *v1, const float *v2, const float *o, const float *d,
                   float tmin, float tmax, float *t, float *u, float *v);

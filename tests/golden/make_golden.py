@@ -24,6 +24,7 @@ from crender_b200 import scenes  # noqa: E402
 
 N_RAYS = 2048
 IMAGES = {"cornell": (32, 32, 4, 8, 3), "mesh": (48, 32, 2, 5, 3), "textured": (40, 30, 3, 6, 3), "terrain": (40, 24, 2, 4, 3)}  # w,h,spp,bounces,seed
+EXT_IMAGES = {"cornell": (32, 32, 4, 8, 3), "textured": (40, 30, 3, 6, 3), "lights": (48, 32, 3, 6, 3)}
 
 
 def build(name):
@@ -53,6 +54,16 @@ def generate():
         out[f"{name}/depth"] = r.current_depths()
         st = r.current_stats()
         out[f"{name}/stats"] = np.asarray([st.total_queries, st.ref_rays, st.pixel_samples, st.passes], np.uint64)
+    # extended shading mode (oracle-specified, see oracle.cpp "EXTENDED shading mode")
+    for name in EXT_IMAGES:
+        desc = scenes.lights_scene(40, 20, n_lights=8) if name == "lights" else common.small_scenes()[name]
+        s = ob.scene()
+        scenes.load(desc, s)
+        s.commit()
+        w, hh, spp, bounces, seed = EXT_IMAGES[name]
+        r = ob.renderer(w, hh, bounces, s, seed=seed, extended=True)
+        r.render(spp, nthreads=1)
+        out[f"{name}/ext_raw"] = r.raw_sum()
     L = ob.lib()
     out["rng"] = np.asarray([L.orc_kat_rng(s_, p, k, d) for s_, p, k, d in [(0, 0, 0, 0), (0, 0, 0, 1), (3, 12345, 7, 5), (9, 2073599, 255, 33)]], np.float32)
     return out

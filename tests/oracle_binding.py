@@ -70,6 +70,9 @@ def lib() -> C.CDLL:
     L.orc_render_create.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.orc_render_destroy.argtypes = [P]
     L.orc_render_reset.argtypes = [P]
+    L.orc_render_set_extended.argtypes = [P, C.c_int]
+    L.orc_kat_scatter_extended.restype = C.c_int
+    L.orc_kat_scatter_extended.argtypes = [C.POINTER(OMaterial), P, P, P, C.c_float, C.c_float, P, P, P]
     L.orc_render_set_rows.argtypes = [P, C.c_uint32, C.c_uint32]
     L.orc_render_samples.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int]
     L.orc_render_read.argtypes = [P, C.c_int, P]
@@ -186,10 +189,12 @@ class scene:
 
 
 class renderer:
-    def __init__(self, res_x, res_y, bounces, scn: scene, seed=0):
+    def __init__(self, res_x, res_y, bounces, scn: scene, seed=0, extended=False):
         self._L = lib()
         self._scene = scn
         self._h = C.c_void_p(self._L.orc_render_create(scn._h, res_x, res_y, bounces, seed))
+        if extended:
+            self._L.orc_render_set_extended(self._h, int(extended))  # 2 = extended without the light list
         self._res = (res_x, res_y)
         self._next = 0
 

@@ -54,10 +54,10 @@ def check_hits(oracle, lib_path, desc, n_rays=20000, exact=False):
     return agree, dt
 
 
-def render_pair(oracle, lib_path, desc, w, h, spp, bounces, seed=3):
+def render_pair(oracle, lib_path, desc, w, h, spp, bounces, seed=3, extended=False):
     o, g = build_pair(oracle, lib_path, desc)
-    ro = oracle.renderer(w, h, bounces, o, seed=seed)
-    rg = api.renderer(w, h, bounces, g, seed=seed)
+    ro = oracle.renderer(w, h, bounces, o, seed=seed, extended=extended)
+    rg = api.renderer(w, h, bounces, g, seed=seed, extended=extended)
     ro.render(spp)
     rg.render(spp)
     return ro, rg
@@ -78,8 +78,8 @@ def check_primary_hits(oracle, lib_path, desc, w, h, exact=False):
     return ph
 
 
-def check_image(oracle, lib_path, desc, w, h, spp, bounces, exact=False):
-    ro, rg = render_pair(oracle, lib_path, desc, w, h, spp, bounces)
+def check_image(oracle, lib_path, desc, w, h, spp, bounces, exact=False, extended=False):
+    ro, rg = render_pair(oracle, lib_path, desc, w, h, spp, bounces, extended=extended)
     a, b = rg.raw_sum(), ro.raw_sum()
     np.testing.assert_array_equal(a[..., 3], b[..., 3])  # pass count
     err = common.relrmse(a[..., :3], b[..., :3])
@@ -334,6 +334,60 @@ def check_material_sort_is_equivalent(lib_path):
     sa, sb = a.current_stats(), b.current_stats()
     assert sa.total_queries == sb.total_queries and sa.ref_rays == sb.ref_rays
     assert sb.kernel_launches > sa.kernel_launches  # the sort is an extra pass per bounce
+
+
+def check_extended_properties(lib_path):
+    """Extended mode: it really is a different shading path, the material sort only reorders work, splitting the
+    sample range or the rows changes no bit, and the light list follows material edits without a rebuild."""
+    desc = scenes.lights_scene(40, 20, n_lights=6)
+    g = api.scene(lib_path=lib_path)
+    ids = scenes.load(desc, g)
+    g.commit()
+    w, h, spp, bounces = 48, 32, 4, 6
+    ref = api.renderer(w, h, bounces, g, seed=4)
+    ref.render(spp)
+    a = api.renderer(w, h, bounces, g, seed=4, extended=True)
+    a.render(spp)
+    whole = a.raw_sum().copy()
+    assert common.relrmse(whole[..., :3], ref.raw_sum()[..., :3]) > 0.05
+    np.testing.assert_array_equal(a.current_normals(), ref.current_normals())  # AOVs are the same first hits
+    b = api.renderer(w, h, bounces, g, seed=4, extended=True, material_sort=True)
+    b.render(spp)
+    np.testing.assert_array_equal(b.raw_sum(), whole)
+    a.start()
+    a.render(1, first_sample=0)
+    a.render(spp - 1, first_sample=1)
+    np.testing.assert_array_equal(a.raw_sum(), whole)
+    a.start()
+    a.set_rows(0, 11)
+    a.render(spp, first_sample=0)
+    a.set_rows(11, h)
+    a.render(spp, first_sample=0)
+    np.testing.assert_array_equal(a.raw_sum()[..., :3], whole[..., :3])
+    # switching the emitters off through a material edit empties the light list: darker image, no rebuild
+    a.set_rows(0, h)
+    mats = [material(api.SMOOTH, colour=(1, 1, 1, 1), emission=0.0, name="emitter-off")]
+
+    def mutate():
+        g.set_materials(ids[-1], mats)
+
+    a.update(mutate)
+    a.render(spp, first_sample=0)
+    assert a.raw_sum()[..., :3].mean() < whole[..., :3].mean()
+    # roughness is live in extended mode (dead in the reference)
+    rough = []
+    for r_ in (0.05, 0.9):
+        d2 = scenes.mesh_scene(24, 12)
+        for m in d2.meshes:
+            for mm in m.materials:
+                mm.roughness = r_
+        g2 = api.scene(lib_path=lib_path)
+        scenes.load(d2, g2)
+        g2.commit()
+        rr = api.renderer(w, h, bounces, g2, seed=4, extended=True)
+        rr.render(2)
+        rough.append(rr.raw_sum().copy())
+    assert not np.array_equal(rough[0], rough[1])
 
 
 def check_query_kinds_consistent(lib_path, desc, n_rays=400000, seeds=(21, 22, 23)):

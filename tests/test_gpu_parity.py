@@ -209,6 +209,14 @@ def test_against_golden_fixtures(product_lib):
             assert ok.mean() >= 0.999, (name, aov, ok.mean())
         st = r.current_stats()
         assert int(st.passes) == int(gold[f"{name}/stats"][3]) and int(st.pixel_samples) == int(gold[f"{name}/stats"][2])
+    for name, (w, hh, spp, bounces, seed) in make_golden.EXT_IMAGES.items():
+        desc = scenes.lights_scene(40, 20, n_lights=8) if name == "lights" else common.small_scenes()[name]
+        g = api.scene(lib_path=product_lib)
+        scenes.load(desc, g)
+        g.commit()
+        r = api.renderer(w, hh, bounces, g, seed=seed, extended=True)
+        r.render(spp)
+        assert common.relrmse(r.raw_sum()[..., :3], gold[f"{name}/ext_raw"][..., :3]) <= pc.IMG_RELRMSE, name
 
 
 def test_checkpoint_resume(product_lib):
@@ -238,3 +246,51 @@ def test_trace_steps_variants_identical(product_lib):
 
 def test_recycled_memory_is_clean(product_lib):
     pc.check_recycled_memory_is_clean(product_lib)
+
+
+# ---- extended shading mode (CRB_RENDER_FLAG_EXTENDED; specified by the oracle, tests/test_extended.py pins it)
+def _ext_scene(name):
+    if name == "lights":
+        return scenes.lights_scene(60, 30, n_lights=16)
+    return common.small_scenes()[name]
+
+
+@pytest.mark.parametrize("name,w,h,spp,bounces", [("cornell", 128, 128, 16, 8), ("mesh", 160, 90, 8, 8), ("textured", 160, 120, 8, 6), ("terrain", 160, 90, 4, 5),
+                                                  ("lights", 160, 90, 8, 6)])
+def test_extended_images_match_oracle(oracle, product_lib, name, w, h, spp, bounces):
+    pc.check_image(oracle, product_lib, _ext_scene(name), w, h, spp, bounces, extended=True)
+
+
+def test_extended_properties(product_lib):
+    pc.check_extended_properties(product_lib)
+
+
+def test_extended_1m_rows_vs_oracle(oracle, product_lib):
+    # BASELINE config 5 geometry (the 1M-triangle mesh + 64 emissive quads) at 1080p, a 16-row band
+    desc = scenes.lights_scene(1000, 500, n_lights=64)
+    g = api.scene(lib_path=product_lib)
+    scenes.load(desc, g)
+    g.commit()
+    o = oracle.scene()
+    scenes.load(desc, o)
+    o.commit()
+    w, h, y0, y1, spp = 1920, 1080, 560, 576, 32
+    ro = oracle.renderer(w, h, 8, o, seed=0, extended=True)
+    ro.set_rows(y0, y1)
+    ro.render(spp)
+    rg = api.renderer(w, h, 8, g, seed=0, extended=True)
+    rg.set_rows(y0, y1)
+    rg.render(spp)
+    a = rg.raw_sum()[h - y1 : h - y0, :, :3]
+    b = ro.raw_sum()[h - y1 : h - y0, :, :3]
+    assert b.mean() > 0 and np.isfinite(a).all()
+    assert common.relrmse(a, b) <= pc.IMG_RELRMSE
+    # full frame, size-independent: splitting the samples changes no bit
+    rg.set_rows(0, h)
+    rg.start()
+    rg.render(4)
+    whole = rg.raw_sum().copy()
+    rg.start()
+    rg.render(3, first_sample=0)
+    rg.render(1, first_sample=3)
+    np.testing.assert_array_equal(rg.raw_sum(), whole)
