@@ -7,6 +7,7 @@ per line on stdout; results are copied into profiles/ per round. (bench.py stays
   python tools/bench_configs.py c1                        config 1: Cornell 512x512, 64 spp, depth 8
   python tools/bench_configs.py c4     [--spp 64]         config 4 geometry: 18M flattened triangles (instanced terrain+city), 1080p
   python tools/bench_configs.py c5     [--spp 16]         config 5 geometry: 1M mesh + 64 emitters, 3840x2160
+  (c1/c2/c4/c5 take --extended: GGX / Fresnel / area-light NEE shading, and --sort: material sort before shading)
   python tools/bench_configs.py mem                       L2 / HBM read bandwidth micro-benchmark
 """
 import argparse
@@ -95,11 +96,11 @@ def cmd_build(a):
         del g
 
 
-def render_rate(desc, w, h, bounces, spp, label, warm=4):
+def render_rate(desc, w, h, bounces, spp, label, warm=4, extended=False, material_sort=False):
     g = api.scene()
     scenes.load(desc, g)
     info = g.commit()
-    r = api.renderer(w, h, bounces, g, seed=0)
+    r = api.renderer(w, h, bounces, g, seed=0, extended=extended, material_sort=material_sort, timers=extended)
     r.render(warm)
     r.start()
     t0 = time.perf_counter()
@@ -109,7 +110,9 @@ def render_rate(desc, w, h, bounces, spp, label, warm=4):
     print(json.dumps({"config": label, "triangles": int(info.n_triangles), "nodes": int(info.n_nodes), "build_ms": info.build_ms, "res": [w, h], "spp": spp,
                       "bounces": bounces, "device_ms": st.device_ms, "wall_ms": wall * 1e3, "mrays_s": st.total_queries / st.device_ms / 1e3,
                       "samples_per_s": st.pixel_samples / (st.device_ms * 1e-3), "rays_per_sample": st.total_queries / st.pixel_samples,
-                      "bvh_bytes": int(info.node_bytes + info.tri_bytes)}), flush=True)
+                      "bvh_bytes": int(info.node_bytes + info.tri_bytes), "shading": "extended" if extended else "ref-exact", "material_sort": bool(material_sort),
+                      **({"kernel_ms": {k: round(st.kernel_ms[i], 3) for i, k in enumerate(("raygen", "trace", "shade", "shadow", "advance", "accumulate"))}} if extended else {})}),
+          flush=True)
 
 
 def cmd_mem(a):
@@ -124,7 +127,9 @@ def cmd_mem(a):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["rays", "build", "c1", "c4", "c5", "mem"])
+    ap.add_argument("cmd", choices=["rays", "build", "c1", "c2", "c4", "c5", "mem"])
+    ap.add_argument("--extended", action="store_true", help="render configs: the extended shading mode (GGX / Fresnel / area-light NEE)")
+    ap.add_argument("--sort", action="store_true", help="render configs: material sort before shading")
     ap.add_argument("--n", type=int, default=100_000_000)
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--no-ground", action="store_true", help="rays: drop the ground quad so that the ray box is the mesh's own box")
@@ -134,10 +139,13 @@ if __name__ == "__main__":
     elif a.cmd == "build":
         cmd_build(a)
     elif a.cmd == "c1":
-        render_rate(scenes.cornell(), 512, 512, 8, a.spp or 64, "1: Cornell 512x512 64 spp depth 8")
+        render_rate(scenes.cornell(), 512, 512, 8, a.spp or 64, "1: Cornell 512x512 64 spp depth 8", extended=a.extended, material_sort=a.sort)
+    elif a.cmd == "c2":
+        render_rate(scenes.mesh_scene(1000, 500), 1920, 1080, 8, a.spp or 32, "2: 1M-triangle mesh, 1080p", extended=a.extended, material_sort=a.sort)
     elif a.cmd == "c4":
-        render_rate(scenes.terrain_city(1000, 3), 1920, 1080, 8, a.spp or 64, "4 (geometry): 18M flattened triangles, 1080p")
+        render_rate(scenes.terrain_city(1000, 3), 1920, 1080, 8, a.spp or 64, "4 (geometry): 18M flattened triangles, 1080p", extended=a.extended, material_sort=a.sort)
     elif a.cmd == "c5":
-        render_rate(scenes.lights_scene(), 3840, 2160, 8, a.spp or 16, "5 (geometry): 1M mesh + 64 emitters, 3840x2160")
+        render_rate(scenes.lights_scene(), 3840, 2160, 8, a.spp or 16, "5: 1M mesh + 64 emitters, 3840x2160" if a.extended else "5 (geometry): 1M mesh + 64 emitters, 3840x2160",
+                    extended=a.extended, material_sort=a.sort)
     else:
         cmd_mem(a)
