@@ -363,11 +363,15 @@ def e2e(a, desc, scene_bytes, api, scenes, local):
     info = g.commit()
     r = api.renderer(a.width, a.height, a.bounces, g, seed=0)
     t1 = time.perf_counter()
+    marks = []
     for k in range(a.steps):
         g.set_camera(desc.cam)  # the step's input
         r.render(spp, first_sample=k * spp)
         r.current_progress(out)
+        marks.append(time.perf_counter())
     t2 = time.perf_counter()
+    if os.environ.get("CRB_BENCH_DEBUG"):
+        sys.stderr.write("e2e step ms: " + " ".join("%.1f" % ((b - a_) * 1e3) for a_, b in zip([t1] + marks[:-1], marks)) + "\n")
     st = r.current_stats()
     q = st.total_queries
     return {

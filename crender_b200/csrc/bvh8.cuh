@@ -76,8 +76,12 @@ namespace crb
     }
 
     __device__ __forceinline__ unsigned byte_of(unsigned w, int i) { return (w >> (8 * i)) & 0xffu; }
-#ifndef CRB_NODE_PRMT
-#define CRB_NODE_PRMT 0    // 0: I2F byte conversion; 1: PRMT into the mantissa for all 48 bytes of a node; 2: for half of them
+// Of the 48 byte->float conversions of a node test, the 16 of CRB_NODE_PRMT_AXES axes go through PRMT + a folded
+// slab FMA on the ALU pipe instead of I2F on the conversion unit (4 lanes/clk/SMSP, the busiest pipe of k_trace at
+// 65 %). Measured on config 2 (profiles/r1g_sweeps.md): 0 axes 2883, 1 axis 2992-3013, 2 axes 2970-2999, 3 axes
+// 2944-2949 Mrays/s: one axis balances the two pipes.
+#ifndef CRB_NODE_PRMT_AXES
+#define CRB_NODE_PRMT_AXES 1
 #endif
     // 1 + q * 2^-15 for byte i of w: the byte lands in bits 8..15 of the bit pattern of 1.0f (one PRMT)
     // `one` must hold 0x3f800000 in a REGISTER the compiler cannot fold (see opaque_one): SASS PRMT has one
@@ -125,14 +129,17 @@ namespace crb
         // computation free of loop-invariant select arms.
         const unsigned octinv4 = octinv * 0x01010101u;
         unsigned       hits    = 0;
-#if CRB_NODE_PRMT
+#if CRB_NODE_PRMT_AXES
         const unsigned one = 0x3f800000u ^ (n1.x >> 31);    // child_base < 2^31: always 1.0f, but not a literal (see byte_as_float)
         // folded slab constants; the offset b - a*2^15 is rounded once (<= |a| * 2^-9, i.e. 1/512 of a grid cell),
         // so the entry side is loosened downwards and the exit side upwards by 1/256 of a cell
-        const float Ax = ax * 32768.0f, Ay = ay * 32768.0f, Az = az * 32768.0f;
-        const float Bnx = (bx - Ax) - fabsf(ax) * 0.00390625f, Bfx = (bx - Ax) + fabsf(ax) * 0.00390625f;
-        const float Bny = (by - Ay) - fabsf(ay) * 0.00390625f, Bfy = (by - Ay) + fabsf(ay) * 0.00390625f;
-        const float Bnz = (bz - Az) - fabsf(az) * 0.00390625f, Bfz = (bz - Az) + fabsf(az) * 0.00390625f;
+        const float Ax = ax * 32768.0f, Bnx = (bx - Ax) - fabsf(ax) * 0.00390625f, Bfx = (bx - Ax) + fabsf(ax) * 0.00390625f;
+#if CRB_NODE_PRMT_AXES >= 2
+        const float Ay = ay * 32768.0f, Bny = (by - Ay) - fabsf(ay) * 0.00390625f, Bfy = (by - Ay) + fabsf(ay) * 0.00390625f;
+#endif
+#if CRB_NODE_PRMT_AXES >= 3
+        const float Az = az * 32768.0f, Bnz = (bz - Az) - fabsf(az) * 0.00390625f, Bfz = (bz - Az) + fabsf(az) * 0.00390625f;
+#endif
 #endif
 #pragma unroll
         for (int half = 0; half < 2; half++)
@@ -149,22 +156,23 @@ namespace crb
 #pragma unroll
             for (int j = 0; j < 4; j++)
             {
-#if CRB_NODE_PRMT
                 // byte -> float without the conversion pipe: PRMT drops the byte into mantissa bits 8..15 of 1.0f
                 // (value 1 + q * 2^-15), and the slab FMA absorbs the offset and the scale: q*a + b ==
-                // (1 + q*2^-15) * (a*2^15) + (b - a*2^15). Same instruction count as I2F + FFMA, but PRMT runs on
-                // the ALU pipe (16 lanes/clk/SMSP) instead of the conversion unit (4 lanes/clk/SMSP).
-                const bool  conv = (CRB_NODE_PRMT == 1) || ((j & 1) == 0);    // 2: half of the bytes stay on I2F
-                const float t0x = conv ? fmaf(byte_as_float(nearx, j, one), Ax, Bnx) : fmaf(float(byte_of(nearx, j)), ax, bx);
-                const float t1x = conv ? fmaf(byte_as_float(farx, j, one), Ax, Bfx) : fmaf(float(byte_of(farx, j)), ax, bx);
-                const float t0y = conv ? fmaf(byte_as_float(neary, j, one), Ay, Bny) : fmaf(float(byte_of(neary, j)), ay, by);
-                const float t1y = conv ? fmaf(byte_as_float(fary, j, one), Ay, Bfy) : fmaf(float(byte_of(fary, j)), ay, by);
-                const float t0z = conv ? fmaf(byte_as_float(nearz, j, one), Az, Bnz) : fmaf(float(byte_of(nearz, j)), az, bz);
-                const float t1z = conv ? fmaf(byte_as_float(farz, j, one), Az, Bfz) : fmaf(float(byte_of(farz, j)), az, bz);
+                // (1 + q*2^-15) * (a*2^15) + (b - a*2^15). Same instruction count as I2F + FFMA.
+#if CRB_NODE_PRMT_AXES >= 1
+                const float t0x = fmaf(byte_as_float(nearx, j, one), Ax, Bnx), t1x = fmaf(byte_as_float(farx, j, one), Ax, Bfx);
 #else
-                const float    t0x = fmaf(float(byte_of(nearx, j)), ax, bx), t1x = fmaf(float(byte_of(farx, j)), ax, bx);
-                const float    t0y = fmaf(float(byte_of(neary, j)), ay, by), t1y = fmaf(float(byte_of(fary, j)), ay, by);
-                const float    t0z = fmaf(float(byte_of(nearz, j)), az, bz), t1z = fmaf(float(byte_of(farz, j)), az, bz);
+                const float t0x = fmaf(float(byte_of(nearx, j)), ax, bx), t1x = fmaf(float(byte_of(farx, j)), ax, bx);
+#endif
+#if CRB_NODE_PRMT_AXES >= 2
+                const float t0y = fmaf(byte_as_float(neary, j, one), Ay, Bny), t1y = fmaf(byte_as_float(fary, j, one), Ay, Bfy);
+#else
+                const float t0y = fmaf(float(byte_of(neary, j)), ay, by), t1y = fmaf(float(byte_of(fary, j)), ay, by);
+#endif
+#if CRB_NODE_PRMT_AXES >= 3
+                const float t0z = fmaf(byte_as_float(nearz, j, one), Az, Bnz), t1z = fmaf(byte_as_float(farz, j, one), Az, Bfz);
+#else
+                const float t0z = fmaf(float(byte_of(nearz, j)), az, bz), t1z = fmaf(float(byte_of(farz, j)), az, bz);
 #endif
                 const float    tn  = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
                 const float    tf  = fminf(fminf(t1x, t1y), fminf(t1z, tmax));

@@ -485,7 +485,10 @@ namespace crb
             return (tangent * (cosf(phi) * sin_h) + n * cos_h) + bitangent * (sinf(phi) * sin_h);
         }
 
-        __global__ void __launch_bounds__(256, 3) k_shade_ext(DScene sc, RenderParams rp, PathState ps)
+        #ifndef CRB_SHADE_EXT_OCC
+#define CRB_SHADE_EXT_OCC 4    // CTAs per SM: 64 registers (12 bytes of spills) so that the 148 x 4 persistent grid is resident
+#endif
+        __global__ void __launch_bounds__(256, CRB_SHADE_EXT_OCC) k_shade_ext(DScene sc, RenderParams rp, PathState ps)
         {
             const uint32_t c0 = ps.counters[CTR_CLASS0], c1 = c0 + ps.counters[CTR_CLASS0 + 1], c2 = c1 + ps.counters[CTR_CLASS0 + 2],
                            n = ps.sorted ? c2 + ps.counters[CTR_CLASS0 + 3] : ps.counters[CTR_IN];
