@@ -9,8 +9,11 @@ workload : configs[1] — procedurally tessellated 1M-triangle mesh (+ ground), 
 value    : device-timed (CUDA events on the library's stream, barrier + sync on both sides, max over
            ranks), scene and BVH already resident in HBM.
 e2e      : the same metric through the public API with HOST buffers: scene arrays host->device, device
-           BVH build, K steps each followed by a device->host read of the display buffer, all inside the
-           timed region (wall clock around synchronous calls).
+           BVH build, K steps each followed by a device->host read of the display buffer into pinned host memory,
+           all inside the timed region (wall clock). The read-back of step k is asynchronous
+           (crb_render_read_async: snapshot after the step's kernels, copy on a second stream) and overlaps the
+           kernels of step k+1; the clock stops after the last image has landed (--e2e-blocking-read: the
+           blocking call after every step instead).
 roofline : dominant kernel = k_trace (closest-hit traversal). achieved = algorithmic bytes per launch /
            mean launch duration (CUDA events around every k_trace launch, CRB_RENDER_FLAG_TIMERS, measured
            in a separate instrumented pass of the same workload so that the headline is not perturbed).
@@ -55,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-blocking-read", action="store_true", help="e2e: read the display buffer back with the blocking call")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
 
@@ -357,19 +361,30 @@ def e2e(a, desc, scene_bytes, api, scenes, local):
     r.render(spp)
     r.current_progress(out)
     del r, g
+    # two pinned host images: the read-back of step k (crb_render_read_async: snapshot after the step's kernels,
+    # device->host on a second stream) overlaps the kernels of step k+1, like the reference's UI thread reading
+    # the live buffers while the workers render; every step's image has landed before the clock stops
+    outs = [out, torch.empty((a.height, a.width, 4), dtype=torch.float32, pin_memory=True).numpy()]
     t0 = time.perf_counter()
     g = api.scene(device=local)
     scenes.load(desc, g)
     info = g.commit()
     r = api.renderer(a.width, a.height, a.bounces, g, seed=0)
     t1 = time.perf_counter()
-    marks = []
+    marks, tickets = [], []
     for k in range(a.steps):
         g.set_camera(desc.cam)  # the step's input
-        r.render(spp, first_sample=k * spp)
-        r.current_progress(out)
+        r.render(spp, first_sample=k * spp, sync=False)
+        if a.e2e_blocking_read:
+            r.current_progress(outs[k & 1])
+        else:
+            if k >= 2:
+                r.wait_read(tickets[k - 2])  # the host buffer about to be overwritten has been consumed
+            tickets.append(r.current_progress_async(outs[k & 1]))
         marks.append(time.perf_counter())
+    r.sync()  # all kernels and all read-backs done
     t2 = time.perf_counter()
+    checksum = float(outs[(a.steps - 1) & 1][::97, ::89, :3].sum())  # touch the last image on the host
     if os.environ.get("CRB_BENCH_DEBUG"):
         sys.stderr.write("e2e step ms: " + " ".join("%.1f" % ((b - a_) * 1e3) for a_, b in zip([t1] + marks[:-1], marks)) + "\n")
     st = r.current_stats()
@@ -377,7 +392,9 @@ def e2e(a, desc, scene_bytes, api, scenes, local):
     return {
         "value": q / (t2 - t0) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes / a.steps + 36), "d2h_bytes_per_step": int(out.nbytes),
         "steady_value": q / (t2 - t1) / 1e6, "setup_ms": (t1 - t0) * 1e3, "bvh_build_ms": info.build_ms, "upload_ms": info.upload_ms,
-        "note": "value includes scene upload + BVH build + per-step display read-back; steady_value excludes the one-off upload/build",
+        "read_back": "blocking" if a.e2e_blocking_read else "asynchronous, overlapped with the next step (crb_render_read_async)",
+        "last_image_checksum": checksum,
+        "note": "value includes scene upload + BVH build + a display read-back into pinned host memory every step; steady_value excludes the one-off upload/build",
     }
 
 

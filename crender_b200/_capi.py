@@ -117,6 +117,8 @@ SIGNATURES = {
     "crb_render_samples": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "crb_render_sync": (C.c_int, [_P]),
     "crb_render_read": (C.c_int, [_P, C.c_int, _P]),
+    "crb_render_read_async": (C.c_int, [_P, C.c_int, _P, C.POINTER(C.c_uint64)]),
+    "crb_render_read_wait": (C.c_int, [_P, C.c_uint64]),
     "crb_render_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "crb_render_restore": (C.c_int, [_P, _P, C.c_uint32]),
     "crb_post_process": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.POINTER(PostSettings), _P]),

@@ -334,6 +334,21 @@ class renderer:
     def current_progress(self, out=None) -> np.ndarray:
         return self._read(PROGRESS, out)
 
+    def current_progress_async(self, out: np.ndarray, kind: int = PROGRESS) -> int:
+        """The reference's UI reads the live buffers while the workers keep rendering (renderer.cpp:220-238):
+        queues a snapshot of the buffer after the work submitted so far and its copy into `out` (pinned host
+        memory for a truly asynchronous copy); returns a ticket for wait_read(). The next render() can be
+        submitted at once, the transfer overlaps it."""
+        w, h = self._res
+        if out.dtype != np.float32 or out.size != w * h * 4 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous float32 array of h*w*4 elements")
+        t = C.c_uint64(0)
+        _capi.check(self._lib, self._lib.crb_render_read_async(self._h, kind, _ptr(out), C.byref(t)))
+        return int(t.value)
+
+    def wait_read(self, ticket: int):
+        _capi.check(self._lib, self._lib.crb_render_read_wait(self._h, ticket))
+
     def current_normals(self) -> np.ndarray:
         return self._read(NORMAL)
 

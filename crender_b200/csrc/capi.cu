@@ -328,6 +328,22 @@ int crb_render_read(crb_render *r, int kind, float *dst)
         r->r.read(kind, dst);
     });
 }
+int crb_render_read_async(crb_render *r, int kind, float *dst, uint64_t *ticket)
+{
+    return guarded([&] {
+        need(r, "render");
+        need(dst, "dst");
+        need(ticket, "ticket");
+        *ticket = r->r.read_async(kind, dst);
+    });
+}
+int crb_render_read_wait(crb_render *r, uint64_t ticket)
+{
+    return guarded([&] {
+        need(r, "render");
+        r->r.read_wait(ticket);
+    });
+}
 int crb_render_stats(crb_render *r, crb_stats *out)
 {
     return guarded([&] {

@@ -852,8 +852,6 @@ namespace crb
 #ifndef CRB_EMU
         CRB_CUDA_CHECK(cudaSetDevice(s->device));
         n_sms = s->n_sms;    // (cudaGetDeviceProperties costs tens of milliseconds; the scene already asked)
-        CRB_CUDA_CHECK(cudaEventCreate(&ev0));
-        CRB_CUDA_CHECK(cudaEventCreate(&ev1));
 #endif
         counters.alloc(CTR_COUNT);
         dstats.alloc(ST_COUNT);
@@ -865,8 +863,11 @@ namespace crb
     {
 #ifndef CRB_EMU
         cudaStreamSynchronize(stream());
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        if (copy_stream) cudaStreamSynchronize(copy_stream), cudaStreamDestroy(copy_stream);
+        if (snap_done) cudaEventDestroy(snap_done);
+        for (cudaEvent_t e : copy_done)
+            if (e) cudaEventDestroy(e);
+        for (const Span &sp : spans) cudaEventDestroy(sp.a), cudaEventDestroy(sp.b);
         for (const Timed &t : timed) cudaEventDestroy(t.a), cudaEventDestroy(t.b);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
 #endif
@@ -932,17 +933,29 @@ namespace crb
         capacity = n;
     }
 
-    void Render::collect_time()
+    void Render::collect_time(bool wait)
     {
 #ifndef CRB_EMU
-        if (ev_pending)
+        // spans complete in stream order: resolve the finished prefix, and everything when asked to wait
+        size_t done = 0;
+        for (; done < spans.size(); done++)
         {
-            CRB_CUDA_CHECK(cudaEventSynchronize(ev1));
+            const Span &sp = spans[done];
+            if (wait)
+                CRB_CUDA_CHECK(cudaEventSynchronize(sp.b));
+            else
+            {
+                const cudaError_t q = cudaEventQuery(sp.b);
+                if (q == cudaErrorNotReady) break;
+                CRB_CUDA_CHECK(q);
+            }
             float ms = 0;
-            CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+            CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, sp.a, sp.b));
             device_ms += ms;
-            ev_pending = false;
+            ev_pool.push_back(sp.a), ev_pool.push_back(sp.b);
         }
+        spans.erase(spans.begin(), spans.begin() + done);
+        if (!wait) return;
         for (const Timed &t : timed)
         {
             CRB_CUDA_CHECK(cudaEventSynchronize(t.b));
@@ -993,7 +1006,7 @@ namespace crb
     {
         if (n == 0) return;
         if (scene_version != scene->version) refresh();
-        collect_time();
+        collect_time(false);
         const uint32_t nrows = row1 - row0;
         const uint32_t npix  = w * nrows;
         static const size_t tp_env = getenv("CRB_TARGET_PATHS") ? size_t(atoll(getenv("CRB_TARGET_PATHS"))) : 0;    // tuning knob
@@ -1034,7 +1047,8 @@ namespace crb
         const unsigned pgrid = 1, pblock = 1;
 #else
         const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256;
-        CRB_CUDA_CHECK(cudaEventRecord(ev0, stream()));
+        const Span span { take_event(), take_event() };
+        CRB_CUDA_CHECK(cudaEventRecord(span.a, stream()));
 #endif
         cudaStream_t st = stream();
         for (uint32_t done = 0; done < n; done += spp_batch)
@@ -1118,14 +1132,17 @@ namespace crb
             pixel_samples += uint64_t(np);
         }
 #ifndef CRB_EMU
-        CRB_CUDA_CHECK(cudaEventRecord(ev1, stream()));
-        ev_pending = true;
+        CRB_CUDA_CHECK(cudaEventRecord(span.b, stream()));
+        spans.push_back(span);
 #endif
     }
 
     void Render::sync()
     {
         stream_sync(stream());
+#ifndef CRB_EMU
+        if (copy_stream) stream_sync(copy_stream);    // "paused" includes every read_async issued so far
+#endif
         collect_time();
     }
 
@@ -1139,20 +1156,67 @@ namespace crb
 #endif
     }
 
+    const float4 *Render::buffer_of(int kind) const
+    {
+        switch (kind)
+        {
+        case CRB_RAW_SUM: return accum.p;
+        case CRB_PROGRESS: return display.p;
+        case CRB_ALBEDO: return albedo.p;
+        case CRB_NORMAL: return normal.p;
+        case CRB_DEPTH: return depth.p;
+        default: throw Error(ERR_INVALID_ARG, "read: unknown buffer kind");
+        }
+    }
+
     void Render::read(int kind, float *dst)
     {
         sync();
-        const float4 *src = nullptr;
-        switch (kind)
+        dev_download(dst, buffer_of(kind), size_t(w) * h * 16, stream());
+    }
+
+    // The reference's UI thread reads the live image buffers while the workers keep rendering
+    // (renderer.cpp:220-238, lock-free). Here: a consistent snapshot is taken on the render stream after the work
+    // queued so far (device-to-device, 33 MB at 1080p = ~10 us), and its device->host copy runs on a second stream,
+    // so the caller can queue the next render_samples right away and the PCIe transfer hides behind it.
+    uint64_t Render::read_async(int kind, float *dst)
+    {
+        const float4 *src   = buffer_of(kind);
+        const size_t  bytes = size_t(w) * h * 16;
+#ifdef CRB_EMU
+        dev_download(dst, src, bytes, stream());
+        return next_ticket++;
+#else
+        if (!copy_stream)
         {
-        case CRB_RAW_SUM: src = accum.p; break;
-        case CRB_PROGRESS: src = display.p; break;
-        case CRB_ALBEDO: src = albedo.p; break;
-        case CRB_NORMAL: src = normal.p; break;
-        case CRB_DEPTH: src = depth.p; break;
-        default: throw Error(ERR_INVALID_ARG, "read: unknown buffer kind");
+            CRB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            CRB_CUDA_CHECK(cudaEventCreateWithFlags(&snap_done, cudaEventDisableTiming));
+            for (cudaEvent_t &e : copy_done) CRB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
-        dev_download(dst, src, size_t(w) * h * 16, stream());
+        if (staging.n != size_t(w) * h)
+        {
+            stream_sync(copy_stream);
+            staging.alloc(size_t(w) * h);
+        }
+        // the one staging buffer is free again once the previous device->host copy has finished
+        if (next_ticket) CRB_CUDA_CHECK(cudaStreamWaitEvent(stream(), copy_done[(next_ticket - 1) % 8], 0));
+        dev_copy(staging.p, src, bytes, stream());
+        CRB_CUDA_CHECK(cudaEventRecord(snap_done, stream()));
+        CRB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, snap_done, 0));
+        CRB_CUDA_CHECK(cudaMemcpyAsync(dst, staging.p, bytes, cudaMemcpyDeviceToHost, copy_stream));
+        CRB_CUDA_CHECK(cudaEventRecord(copy_done[next_ticket % 8], copy_stream));
+        return next_ticket++;
+#endif
+    }
+
+    void Render::read_wait(uint64_t ticket)
+    {
+        if (ticket >= next_ticket) throw Error(ERR_INVALID_ARG, "read_wait: unknown ticket");
+#ifndef CRB_EMU
+        // copies complete in order on one stream: a ticket older than the event ring is covered by any newer one
+        const uint64_t t = next_ticket - ticket > 8 ? next_ticket - 8 : ticket;
+        CRB_CUDA_CHECK(cudaEventSynchronize(copy_done[t % 8]));
+#endif
     }
 
     void Render::restore(const float *raw_sum_rgba, uint32_t passes_)

@@ -70,8 +70,22 @@ namespace crb
         double   kernel_ms[8]    = {};
         uint64_t kernel_count[8] = {};
 #ifndef CRB_EMU
-        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-        bool        ev_pending = false;
+        // one event pair per render_samples call; resolved without blocking when the next call is queued
+        // (a blocking wait here would serialise the host's launch work with the device), blocking at sync()
+        struct Span
+        {
+            cudaEvent_t a, b;
+        };
+        std::vector<Span> spans;
+        // asynchronous read-back (read_async / read_wait): snapshot on the render stream, device->host copy on
+        // its own stream so that it overlaps the next render_samples call
+        cudaStream_t copy_stream = nullptr;
+        cudaEvent_t  snap_done   = nullptr;
+        cudaEvent_t  copy_done[8] = {};
+#endif
+        DBuf<float4> staging;
+        uint64_t     next_ticket = 0;
+#ifndef CRB_EMU
         // CRB_RENDER_FLAG_TIMERS: event pairs around every launch, resolved at sync()
         struct Timed
         {
@@ -96,12 +110,15 @@ namespace crb
         void sync();
         void resolve();
         void read(int kind, float *dst);
+        uint64_t read_async(int kind, float *dst);
+        void     read_wait(uint64_t ticket);
         void restore(const float *raw_sum_rgba, uint32_t passes_);
         void stats(crb_stats &out);
 
     private:
         void alloc_images();
         void ensure_paths(size_t n);
-        void collect_time();
+        void collect_time(bool wait = true);
+        const float4 *buffer_of(int kind) const;
     };
 }    // namespace crb

@@ -264,6 +264,15 @@ namespace crb
             return s;
         }
         std::array<uint64_t, 2> current_resolution() const noexcept { return { _res_x, _res_y }; }
+        // live read while rendering goes on (the reference's lock-free getters, renderer.cpp:220-238): snapshot after
+        // the work submitted so far, copied into dst (w*h*4 floats, pinned memory for a truly asynchronous copy)
+        uint64_t current_progress_async(float *dst, int kind = CRB_PROGRESS)
+        {
+            uint64_t ticket = 0;
+            check(crb_render_read_async(_h, kind, dst, &ticket));
+            return ticket;
+        }
+        void wait_read(uint64_t ticket) { check(crb_render_read_wait(_h, ticket)); }
 
     private:
         image read(int kind)

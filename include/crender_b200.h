@@ -210,6 +210,13 @@ enum { CRB_RAW_SUM = 0, CRB_PROGRESS = 1, CRB_ALBEDO = 2, CRB_NORMAL = 3, CRB_DE
 /* current_progress/normals/albedos/depths (renderer.cpp:220-238): w*h*4 floats, row-major, x/y
  * flipped exactly as the reference stores them. CRB_RAW_SUM = _raw_buffer as RGBA with A = passes. */
 int crb_render_read(crb_render *, int kind, float *dst_host);
+/* The reference's UI thread reads those buffers while the workers keep rendering (lock-free getters,
+ * renderer.cpp:220-238; display loop src/display/display.cpp:200-220). crb_render_read_async queues a consistent
+ * snapshot of the buffer after the work submitted so far and copies it to dst_host (pinned memory for a truly
+ * asynchronous copy) on a second stream, so the caller can submit the next crb_render_samples at once;
+ * crb_render_read_wait blocks until the copy of that ticket has landed. crb_render_sync also waits for all of them. */
+int crb_render_read_async(crb_render *, int kind, float *dst_host, uint64_t *ticket);
+int crb_render_read_wait(crb_render *, uint64_t ticket);
 int crb_render_stats(crb_render *, crb_stats *out); /* renderer::current_stats, renderer.cpp:396-404 */
 /* checkpoint / resume (the reference restarts from 0 spp on every start(), renderer.cpp:154-170): a
  * CRB_RAW_SUM read is a complete checkpoint; restore uploads it (w*h*4 floats) with its pass count, after

@@ -5,6 +5,7 @@ seeds)."""
 import ctypes as C
 
 import numpy as np
+import pytest
 
 import common
 from crender_b200 import _capi, api, scenes
@@ -288,6 +289,49 @@ def check_checkpoint_resume(lib_path):
     r3.render(3)  # continues at first_sample = 5
     np.testing.assert_array_equal(r3.raw_sum(), whole_raw)
     np.testing.assert_array_equal(r3.current_progress(), whole_disp)
+
+
+def check_async_read(lib_path):
+    """crb_render_read_async / crb_render_read_wait: a read queued between two render calls returns the image
+    as it was after the FIRST (snapshot in stream order), bit-identical to the blocking read, while the second
+    call is already submitted; tickets older than the event ring are still waitable; bad tickets fail."""
+    desc = scenes.mesh_scene(40, 20)
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    ref = api.renderer(96, 54, 5, g, seed=9)
+    want = []
+    for k in range(12):
+        ref.render(2)
+        want.append((ref.current_progress().copy(), ref.raw_sum().copy()))
+    r = api.renderer(96, 54, 5, g, seed=9)
+    outs = [np.zeros((54, 96, 4), np.float32) for _ in range(12)]
+    raws = [np.zeros((54, 96, 4), np.float32) for _ in range(12)]
+    tickets = []
+    for k in range(12):
+        r.render(2, sync=False)
+        tickets.append((r.current_progress_async(outs[k]), r.current_progress_async(raws[k], kind=api.RAW_SUM)))
+    r.wait_read(tickets[0][0])  # 24 reads issued: older than the 8-deep event ring
+    np.testing.assert_array_equal(outs[0], want[0][0])
+    for k in range(12):
+        r.wait_read(tickets[k][1])
+        np.testing.assert_array_equal(outs[k], want[k][0])
+        np.testing.assert_array_equal(raws[k], want[k][1])
+    assert tickets[-1][1] == 23
+    with pytest.raises(Exception):
+        r.wait_read(24)
+    with pytest.raises(ValueError):
+        r.current_progress_async(np.zeros((10, 10, 4), np.float32))
+    # sync() covers outstanding reads; a resolution change afterwards re-sizes the staging buffer
+    r.render(1, sync=False)
+    t = r.current_progress_async(outs[0])
+    r.sync()
+    r.set_resolution(48, 27)
+    r.start()
+    r.render(2)
+    small = np.zeros((27, 48, 4), np.float32)
+    r.wait_read(r.current_progress_async(small))
+    np.testing.assert_array_equal(small, r.current_progress())
 
 
 def check_post_chain(lib_path):

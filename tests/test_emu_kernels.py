@@ -43,6 +43,10 @@ def test_checkpoint_resume(emu_lib):
     pc.check_checkpoint_resume(emu_lib)
 
 
+def test_async_read(emu_lib):
+    pc.check_async_read(emu_lib)
+
+
 def test_post_chain(emu_lib):
     pc.check_post_chain(emu_lib)
 

@@ -223,6 +223,10 @@ def test_checkpoint_resume(product_lib):
     pc.check_checkpoint_resume(product_lib)
 
 
+def test_async_read(product_lib):
+    pc.check_async_read(product_lib)
+
+
 def test_post_chain(product_lib):
     pc.check_post_chain(product_lib)
 
