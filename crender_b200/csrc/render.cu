@@ -180,8 +180,12 @@ namespace crb
         // ------------------------------------------------------------------ trace + material sort
         constexpr int TRACE_STEPS = 4;    // node iterations between two refill points of the persistent trace loop
 
+        // resident CTAs per SM of the two traversal kernels (4 = 64 registers; measured alternatives in profiles/)
+#ifndef CRB_TRACE_OCC
+#define CRB_TRACE_OCC 4
+#endif
         template<bool COUNT, int STEPS>
-        __global__ void __launch_bounds__(256, 4) k_trace(DScene sc, PathState ps)
+        __global__ void __launch_bounds__(256, CRB_TRACE_OCC) k_trace(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_IN];
             TravCounters   tc;
@@ -706,7 +710,7 @@ namespace crb
         // ------------------------------------------------------------------ K8 shadow rays
         // sun visibility without alpha cut-outs: any-hit through the persistent trace loop
         template<bool COUNT, int STEPS>
-        __global__ void __launch_bounds__(256, 4) k_shadow(DScene sc, PathState ps)
+        __global__ void __launch_bounds__(256, CRB_TRACE_OCC) k_shadow(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_SHADOW];
             TravCounters   tc;
@@ -1044,9 +1048,9 @@ namespace crb
         const bool count = (flags & CRB_RENDER_FLAG_COUNTERS) != 0;
         static const int steps = getenv("CRB_TRACE_STEPS") ? atoi(getenv("CRB_TRACE_STEPS")) : TRACE_STEPS;    // tuning knob
 #ifdef CRB_EMU
-        const unsigned pgrid = 1, pblock = 1;
+        const unsigned pgrid = 1, pblock = 1, tgrid = 1;
 #else
-        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256;
+        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC;
         const Span span { take_event(), take_event() };
         CRB_CUDA_CHECK(cudaEventRecord(span.a, stream()));
 #endif
@@ -1073,15 +1077,15 @@ namespace crb
                 rp.bounce = i;
                 tick(CRB_K_TRACE);
                 if (count)
-                    CRB_LAUNCH((k_trace<true, TRACE_STEPS>), pgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<true, TRACE_STEPS>), tgrid, pblock, st, dscene, ps);
                 else if (steps == 1)
-                    CRB_LAUNCH((k_trace<false, 1>), pgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 1>), tgrid, pblock, st, dscene, ps);
                 else if (steps == 2)
-                    CRB_LAUNCH((k_trace<false, 2>), pgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 2>), tgrid, pblock, st, dscene, ps);
                 else if (steps == 8)
-                    CRB_LAUNCH((k_trace<false, 8>), pgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 8>), tgrid, pblock, st, dscene, ps);
                 else
-                    CRB_LAUNCH((k_trace<false, 4>), pgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 4>), tgrid, pblock, st, dscene, ps);
                 tock();
                 tick(CRB_K_SHADE);
                 if (ps.sorted) CRB_LAUNCH(k_classify, pgrid, pblock, st, dscene, ps);
@@ -1102,15 +1106,15 @@ namespace crb
                             CRB_LAUNCH((k_shadow_alpha<false>), pgrid, pblock, st, dscene, ps);
                     }
                     else if (count)
-                        CRB_LAUNCH((k_shadow<true, TRACE_STEPS>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<true, TRACE_STEPS>), tgrid, pblock, st, dscene, ps);
                     else if (steps == 1)
-                        CRB_LAUNCH((k_shadow<false, 1>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 1>), tgrid, pblock, st, dscene, ps);
                     else if (steps == 2)
-                        CRB_LAUNCH((k_shadow<false, 2>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 2>), tgrid, pblock, st, dscene, ps);
                     else if (steps == 8)
-                        CRB_LAUNCH((k_shadow<false, 8>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 8>), tgrid, pblock, st, dscene, ps);
                     else
-                        CRB_LAUNCH((k_shadow<false, 4>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 4>), tgrid, pblock, st, dscene, ps);
                     tock();
                     launches++;
                 }
