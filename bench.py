@@ -204,15 +204,16 @@ def run_ours(a):
     stream = torch.cuda.ExternalStream(r.stream(), device=torch.device("cuda", local))
     merged = torch.empty(npix * 4, dtype=torch.float32, device="cuda") if world > 1 else None
 
-    def step(k):
+    def step(k, into=None):
         # global sample indices of step k: rank-major inside the step (weak scaling: spp per rank per step)
         first = (k * world + rank) * spp
         r.render(spp, first_sample=first, sync=False)
         if world > 1:
             # flush: merge the per-rank accumulation buffers (sum over ranks) into `merged`
+            m = merged if into is None else into
             with torch.cuda.stream(stream):
-                merged.copy_(D.accum_tensor(r), non_blocking=True)
-                dist.all_reduce(merged, op=dist.ReduceOp.SUM)
+                m.copy_(D.accum_tensor(r), non_blocking=True)
+                dist.all_reduce(m, op=dist.ReduceOp.SUM)
 
     def barrier():
         torch.cuda.synchronize()
@@ -399,23 +400,46 @@ def e2e(a, desc, scene_bytes, api, scenes, local):
 
 
 def e2e_multi(a, r, step, merged, barrier, torch, dist, world):
-    host = torch.empty(merged.shape, dtype=torch.float32, pin_memory=True)
+    """N > 1: the same step loop, wall-clocked, plus a device->host read of the merged buffer on every rank every step.
+    Two merged buffers and two pinned host images alternate, so the read-back of step k (own copy stream, ordered
+    after the step's all-reduce by an event) overlaps the kernels of step k+1; the clock stops after the last image
+    has landed (--e2e-blocking-read: synchronise and copy after every step instead)."""
+    hosts = [torch.empty(merged.shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    bufs = [merged, torch.empty_like(merged)]
+    stream = torch.cuda.ExternalStream(r.stream(), device=merged.device)
+    copy_stream = torch.cuda.Stream(device=merged.device)
+    done = [None, None]
     barrier()
     q0 = r.current_stats().total_queries
     t0 = time.perf_counter()
     for k in range(a.steps):
-        step(a.warmup + a.steps + k)
-        r.sync()
-        torch.cuda.synchronize()
-        host.copy_(merged)
-    barrier()
+        b = k & 1
+        if a.e2e_blocking_read:
+            step(a.warmup + a.steps + k, bufs[b])
+            r.sync()
+            torch.cuda.synchronize()
+            hosts[b].copy_(bufs[b])
+            continue
+        if done[b] is not None:
+            done[b].synchronize()  # step k-2's image has landed: its device and host buffers are free again
+        step(a.warmup + a.steps + k, bufs[b])
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        copy_stream.wait_event(ready)
+        with torch.cuda.stream(copy_stream):
+            hosts[b].copy_(bufs[b], non_blocking=True)
+            done[b] = torch.cuda.Event()
+            done[b].record(copy_stream)
+    barrier()  # torch.cuda.synchronize() covers the library stream and the copy stream
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     c = torch.tensor([r.current_stats().total_queries - q0], dtype=torch.int64, device="cuda")
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     return {"value": int(c.item()) / float(t.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 36, "d2h_bytes_per_step": int(merged.numel() * 4),
-            "note": "per step: render + NCCL all-reduce of the accumulation buffers + device->host read of the merged buffer on every rank"}
+            "read_back": "blocking" if a.e2e_blocking_read else "asynchronous, overlapped with the next step",
+            "last_image_checksum": float(hosts[(a.steps - 1) & 1][::997].sum()),
+            "note": "per step: render + NCCL all-reduce of the accumulation buffers + device->host read of the merged buffer into pinned host memory on every rank"}
 
 
 _RESULT_FD = None
