@@ -5,7 +5,10 @@
 //
 //   g++ -std=c++17 -O2 crender_cli.cpp -o crender_cli -L.. -lcrender_b200 -Wl,-rpath,'$ORIGIN/..'
 //   ./crender_cli out.bin [w h spp bounces seed]
-#include "crender.hpp"
+//   ./crender_cli --obj model.obj name PNG|HDR|EXR [w h spp bounces]     what the reference's "load model" + "export"
+//                 panels do (src/ui/ui.h:567-631, asset_loader.cpp:182-377): OBJ/MTL/PNG textures in, ./out/name.ext out,
+//                 camera on the -Z side framing the model's bounds, default sun
+#include "assets.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -60,8 +63,49 @@ namespace
     }
 }    // namespace
 
+static int render_obj(int argc, char **argv)
+{
+    namespace al = crb::asset_loader;
+    const std::string file = argv[2], name = argc > 3 ? argv[3] : "render", t = argc > 4 ? argv[4] : "PNG";
+    const int w = argc > 5 ? atoi(argv[5]) : 640, h = argc > 6 ? atoi(argv[6]) : 360, spp = argc > 7 ? atoi(argv[7]) : 64, bounces = argc > 8 ? atoi(argv[8]) : 5;
+    const crb::model_data m = al::load_model(file);
+    if (m.vertices.empty() || m.vertex_indices.empty()) throw crb::error(CRB_ERR_INVALID_ARG, "the OBJ file has no faces");
+    vec3 lo = m.vertices[0], hi = m.vertices[0];
+    for (const vec3 &v : m.vertices)
+        for (int k = 0; k < 3; k++) lo[k] = std::fmin(lo[k], v[k]), hi[k] = std::fmax(hi[k], v[k]);
+    crb::scene scn;
+    scn.add_model(m);
+    crb::camera cam;
+    const float ext = std::fmax(hi[0] - lo[0], hi[1] - lo[1]);
+    cam.fov         = 40.0f;
+    cam.position    = { 0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), lo[2] - 0.75f * ext / std::tan(20.0f * float(M_PI) / 180.0f) - 0.05f * ext };
+    scn.set_camera(cam);
+    const crb_build_info info = scn.commit();
+    crb::renderer        r(uint64_t(w), uint64_t(h), uint64_t(bounces), &scn, 0);
+    r.set_target_spp(uint64_t(spp));
+    r.start();
+    const crb_stats   st   = r.current_stats();
+    const std::string path = al::export_framebuffer(r.current_progress(), name, t == "EXR" ? al::image_type::EXR : t == "HDR" ? al::image_type::HDR : al::image_type::PNG);
+    std::printf("%s: %llu triangles, %llu materials, %llu textures, build %.3f ms, %d spp at %dx%d in %.3f ms device time (%.1f Mrays/s) -> %s\n", m.name.c_str(),
+                (unsigned long long) info.n_triangles, (unsigned long long) m.materials.size(), (unsigned long long) m.textures.size(), info.build_ms, spp, w, h,
+                st.device_ms, st.device_ms > 0 ? double(st.total_queries) / st.device_ms / 1e3 : 0.0, path.c_str());
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 2 && std::string(argv[1]) == "--obj")
+    {
+        try
+        {
+            return render_obj(argc, argv);
+        }
+        catch (const crb::error &e)
+        {
+            std::fprintf(stderr, "crender_cli: error %d: %s\n", e.code, e.what());
+            return e.code;
+        }
+    }
     const char *out = argc > 1 ? argv[1] : "cornell.bin";
     const int   w = argc > 2 ? atoi(argv[2]) : 256, h = argc > 3 ? atoi(argv[3]) : 256, spp = argc > 4 ? atoi(argv[4]) : 16;
     const int   bounces = argc > 5 ? atoi(argv[5]) : 8, seed = argc > 6 ? atoi(argv[6]) : 0;

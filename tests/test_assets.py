@@ -109,3 +109,106 @@ def test_export_exr(tmp_path):
     assert back[0, 1, 2] == -2.5 and abs(back[0, 1, 1] - 6e-6) < 6e-8
     # second export of the same name gets the " (1)" suffix like every other format
     assert assets.export_framebuffer(img, "frame", assets.EXR, out_dir=str(tmp_path)).endswith("frame (1).exr")
+
+
+# ---------------------------------------------------------------------------------------------- C++ host (assets.hpp)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "crender_b200", "host", "assets_tool")
+
+
+def _tool(*args):
+    import subprocess
+
+    import pytest
+
+    if not os.path.exists(TOOL):
+        pytest.fail(f"{TOOL} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    r = subprocess.run([TOOL, *args], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r.stdout.strip()
+
+
+def _read_dump(path):
+    raw = open(path, "rb").read()
+    c = np.frombuffer(raw[:56], np.uint64).astype(int)
+    pos = 56
+
+    def take(n, dt):
+        nonlocal pos
+        a = np.frombuffer(raw[pos : pos + n * np.dtype(dt).itemsize], dt)
+        pos += a.nbytes
+        return a
+
+    d = {"vertices": take(c[0] * 3, np.float32).reshape(-1, 3), "texture_coords": take(c[1] * 2, np.float32).reshape(-1, 2),
+         "vertex_indices": take(c[2], np.uint32), "texture_indices": take(c[3], np.uint32), "material_indices": take(c[4], np.uint32),
+         "materials": [], "textures": []}
+    for _ in range(c[5]):
+        rec = take(6, np.float32)
+        typ, ln = take(2, np.uint32)
+        name = raw[pos : pos + ln].decode()
+        pos += int(ln)
+        d["materials"].append((tuple(rec[:4]), float(rec[4]), int(rec[5]), int(typ), name))
+    for _ in range(c[6]):
+        w, h = take(2, np.uint64).astype(int)
+        d["textures"].append(take(w * h * 4, np.float32).reshape(h, w, 4))
+    assert pos == len(raw)
+    return d
+
+
+def _same_model(tmp_path, obj_name):
+    md = assets.load_model(str(tmp_path / obj_name))
+    name = _tool("load", str(tmp_path / obj_name), str(tmp_path / "dump.bin"))
+    d = _read_dump(tmp_path / "dump.bin")
+    assert name == md.name
+    for k in ("vertices", "texture_coords", "vertex_indices", "texture_indices", "material_indices"):
+        np.testing.assert_array_equal(d[k], getattr(md, k), err_msg=k)
+    assert len(d["materials"]) == len(md.materials) and len(d["textures"]) == len(md.textures)
+    for (col, emission, tex, typ, nm), m in zip(d["materials"], md.materials):
+        assert col == tuple(np.float32(x) for x in m.colour) and emission == m.emission and typ == m.shade_type and nm == m.name
+        assert tex == (-1 if m.tex is None else m.tex)
+    for a, b in zip(d["textures"], md.textures):
+        np.testing.assert_array_equal(a, b)
+    return md
+
+
+def test_cpp_load_model_matches_python(tmp_path):
+    (tmp_path / "test.obj").write_text(OBJ + "f -5/-4 -4/-3 -3/-2\n")  # + a face with negative (relative) indices
+    (tmp_path / "test.mtl").write_text(MTL + "newmtl pal\nKd 0.5 0.5 0.5\nmap_Kd -s 1 1 1 pal.png\nnewmtl again\nmap_Kd tex.png\nnewmtl gone\nmap_Kd missing.png\n")
+    rng = np.random.default_rng(4)
+    tex = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)  # compressed by PIL with dynamic Huffman blocks and filters
+    Image.fromarray(tex, "RGBA").save(tmp_path / "tex.png")
+    Image.fromarray(rng.integers(0, 256, (16, 16), dtype=np.uint8), "L").convert("P").save(tmp_path / "pal.png")  # palette PNG
+    md = _same_model(tmp_path, "test.obj")
+    assert len(md.textures) == 2 and md.materials[3].tex == md.materials[1].tex and md.materials[4].tex is None
+    (tmp_path / "m.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    _same_model(tmp_path, "m.obj")
+    # gradient images exercise the PNG filters; RGB and grey+alpha colour types
+    g = np.add.outer(np.arange(40), np.arange(64)).astype(np.uint8)
+    Image.fromarray(np.stack([g, g.T[:40, :64] if False else g[::-1], g // 2], -1), "RGB").save(tmp_path / "tex.png")
+    Image.fromarray(np.stack([g, 255 - g], -1), "LA").save(tmp_path / "pal.png")
+    _same_model(tmp_path, "test.obj")
+
+
+def test_cpp_export_matches_python(tmp_path):
+    rng = np.random.default_rng(7)
+    img = rng.random((19, 23, 4), dtype=np.float32) * 1.3 - 0.1  # some values outside [0, 1]
+    img[0, 0] = [0.0, 1.0, 0.5, 1.0]
+    img[0, 1] = [1e-4, 65504.0, 1e6, 1.0]  # half denormal / max / overflow
+    with open(tmp_path / "img.bin", "wb") as f:
+        f.write(np.array([23, 19], np.int32).tobytes() + img.tobytes())
+    out = str(tmp_path / "out")
+    p_png = _tool("export", str(tmp_path / "img.bin"), "shot", "PNG", out)
+    assert p_png.endswith("shot.png")
+    np.testing.assert_array_equal(np.asarray(Image.open(p_png)), assets._to_bytes(img))
+    assert _tool("export", str(tmp_path / "img.bin"), "shot", "PNG", out).endswith("shot (1).png")  # collision rule
+    pos = np.clip(img, 0.0, None)
+    with open(tmp_path / "pos.bin", "wb") as f:
+        f.write(np.array([23, 19], np.int32).tobytes() + pos.tobytes())
+    p_hdr = _tool("export", str(tmp_path / "pos.bin"), "shot", "HDR", out)
+    ref_hdr = assets.export_framebuffer(pos, "ref", assets.HDR, out_dir=out)
+    a, b = assets.read_hdr(p_hdr), assets.read_hdr(ref_hdr)
+    # libm powf vs numpy power may differ in the last ulp, which can move an 8-bit mantissa by one step
+    assert np.abs(a - b).max() <= np.maximum(a, b).max(axis=-1, keepdims=True).max() / 128.0 and (a != b).mean() < 0.01
+    p_exr = _tool("export", str(tmp_path / "img.bin"), "shot", "EXR", out)
+    ref_exr = assets.export_framebuffer(img, "ref", assets.EXR, out_dir=out)
+    np.testing.assert_array_equal(assets.read_exr(p_exr), assets.read_exr(ref_exr))

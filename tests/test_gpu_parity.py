@@ -169,6 +169,41 @@ def test_cpp_host_mirror_cli_matches_python_api(product_lib, tmp_path):
     assert common.relrmse(img[..., :3], ref[..., :3]) < 1e-6
 
 
+def test_cpp_host_obj_to_png(product_lib, tmp_path):
+    """OBJ/MTL/PNG texture -> C++ host loader (assets.hpp) -> render -> PNG export, against the Python host doing the same
+    through assets.load_model / export_framebuffer (same library underneath: identical bytes)."""
+    import os
+    import subprocess
+
+    from PIL import Image
+
+    from crender_b200 import assets
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "crender_b200", "host", "crender_cli")
+    (tmp_path / "m.obj").write_text("mtllib m.mtl\nv -1 -1 0\nv 1 -1 0\nv 1 1 0\nv -1 1 0\nv -1 -1 -1\nv 1 -1 -1\nv 1 -1 1\nv -1 -1 1\n"
+                                    "vt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nusemtl tex\nf 1/1 2/2 3/3 4/4\nusemtl red\nf 5/1 6/2 7/3 8/4\n")
+    (tmp_path / "m.mtl").write_text("newmtl tex\nKd 1 1 1\nmap_Kd t.png\nnewmtl red\nKd 0.8 0.2 0.1\n")
+    rng = np.random.default_rng(2)
+    Image.fromarray(rng.integers(0, 256, (8, 8, 4), dtype=np.uint8) | np.array([0, 0, 0, 255], np.uint8), "RGBA").save(tmp_path / "t.png")
+    r = subprocess.run([cli, "--obj", str(tmp_path / "m.obj"), "shot", "PNG", "96", "64", "8", "4"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.asarray(Image.open(tmp_path / "out" / "shot.png"))
+    md = assets.load_model(str(tmp_path / "m.obj"))
+    g = api.scene(lib_path=product_lib)
+    g.add_model(md)
+    lo, hi = md.vertices.min(0), md.vertices.max(0)
+    ext = np.float32(max(hi[0] - lo[0], hi[1] - lo[1]))
+    z = np.float32(lo[2]) - np.float32(0.75) * ext / np.float32(np.tan(np.float32(20.0 * np.pi / 180.0))) - np.float32(0.05) * ext
+    g.set_camera(api.camera(position=(float(0.5 * (lo[0] + hi[0])), float(0.5 * (lo[1] + hi[1])), float(z)), fov=40.0))
+    g.commit()
+    rr = api.renderer(96, 64, 4, g, seed=0)
+    rr.render(8)
+    want = assets._to_bytes(rr.current_progress())
+    assert got.shape == want.shape and (got != want).mean() < 0.01  # camera z may differ by an ulp between the two hosts
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 64
+
+
 def test_update_semantics(oracle, product_lib):
     pc.check_update_semantics(oracle, product_lib)
 
