@@ -24,6 +24,14 @@
 #include "platform.cuh"
 #include "vecmath.cuh"
 
+// compile-time variants of the traversal loop (measured in profiles/r1g_sweeps.md)
+#ifndef CRB_TRI_BRANCHFREE
+#define CRB_TRI_BRANCHFREE 1    // +3.1 % (profiles/r1g_sweeps.md section 6)
+#endif
+#ifndef CRB_EARLY_POP
+#define CRB_EARLY_POP 0
+#endif
+
 namespace crb
 {
     constexpr int      BVH8_STACK      = 48;     // entries; the builder rejects deeper trees loudly
@@ -55,6 +63,21 @@ namespace crb
     //   t = (e2.q)*inv; accept iff 0<=u<=1, v>=0, u+v<=1, tnear < t <= tfar (Embree's convention).
     __device__ __forceinline__ bool tri_test(V3 v0, V3 e1, V3 e2, V3 o, V3 d, float tnear, float tfar, float &t, float &u, float &v)
     {
+#if CRB_TRI_BRANCHFREE
+        // Same operations and roundings, no early exits: in the lock-step leaf phase some lane always runs the whole
+        // test, so the exits only cost branch overhead — and ptxas sank the v0 load below the det branch, i.e. a second
+        // serialised memory wait per leaf test (ncu: 13 % + 5 % of k_trace's stall samples on the two waits).
+        // det == 0 gives inv = inf and NaN/inf in u, v, t; the det test is part of the final predicate.
+        const V3    p   = cross(d, e2);
+        const float det = dot(e1, p);
+        const float inv = __frcp_rn(det);
+        const V3    s   = o - v0;
+        u               = __fmul_rn(dot(s, p), inv);
+        const V3 q      = cross(s, e1);
+        v               = __fmul_rn(dot(d, q), inv);
+        t               = __fmul_rn(dot(e2, q), inv);
+        return (det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (__fadd_rn(u, v) <= 1.0f) & (t > tnear) & (t <= tfar);
+#else
         const V3    p   = cross(d, e2);
         const float det = dot(e1, p);
         if (det == 0.0f) return false;
@@ -67,6 +90,7 @@ namespace crb
         if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
         t = __fmul_rn(dot(e2, q), inv);
         return t > tnear && t <= tfar;
+#endif
     }
 
     __device__ __forceinline__ float safe_rcp(float d)
@@ -283,6 +307,7 @@ namespace crb
         const uint32_t total_warps = (gridDim.x * blockDim.x + CRB_WARP - 1) / CRB_WARP;
         uint32_t       chunk       = n / (total_warps * 4u);
         chunk                      = chunk < uint32_t(CRB_WARP) ? uint32_t(CRB_WARP) : (chunk > chunk_max ? chunk_max : chunk);
+        if (chunk_max && chunk_max < uint32_t(CRB_WARP)) chunk = chunk_max;    // small fixed look-ahead (experiments)
 
         for (;;)
         {
@@ -297,7 +322,7 @@ namespace crb
                 const uint32_t need = uint32_t(__popc(idle));
                 if (local_next == local_end)
                 {
-                    const uint32_t want = chunk_max ? chunk : need;    // chunk_max == 0: reserve exactly what is idle
+                    const uint32_t want = chunk_max ? (chunk > need ? chunk : need) : need;    // chunk_max == 0: reserve exactly what is idle
                     uint32_t       b    = 0;
                     if (lane == 0) b = atomicAdd(cursor, want);
                     b          = __shfl_sync(FULL, b, 0);
@@ -355,6 +380,14 @@ namespace crb
                     group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
                     tgroup           = make_uint2(n1.y, h & 0x00ffffffu);
                 }
+#if CRB_EARLY_POP
+                // ---- pop BEFORE the leaf phase: a lane whose node group has no inner child left will need the next
+                // stack entry as soon as its waiting triangles are done, and `group` is dead until then, so the
+                // local-memory load is issued here and its latency hides behind the leaf phase (ncu: 20 % of k_trace's
+                // long-scoreboard stalls sat on a pop whose value the next instruction used). Visit order unchanged:
+                // the node phase runs only once tgroup is empty.
+                if (active && (group.y & 0xff000000u) == 0u && sp > 0) group = stack[--sp];
+#endif
                 // ---- leaf phase in lock step: ONE triangle per lane that has triangles waiting (an inner
                 // per-lane triangle loop was 52 % of k_trace's instructions at 2.7 active lanes; waiting for
                 // more lanes to have triangles was measured and is slower, profiles/r1c_sweeps.md §6)
@@ -387,6 +420,11 @@ namespace crb
                 // ---- advance: nothing left in this node group -> pop, or retire the ray
                 if (active && tgroup.y == 0u && (group.y & 0xff000000u) == 0u)
                 {
+#if CRB_EARLY_POP
+                    // the early pop found the stack empty (or an any-hit dropped everything): retire
+                    if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
+                    active = false, finished = true;
+#else
                     if (sp == 0)
                     {
                         if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
@@ -394,6 +432,7 @@ namespace crb
                     }
                     else
                         group = stack[--sp];
+#endif
                 }
             }
         }
