@@ -29,7 +29,7 @@
 #define CRB_TRI_BRANCHFREE 1    // +3.1 % (profiles/r1g_sweeps.md section 6)
 #endif
 #ifndef CRB_EARLY_POP
-#define CRB_EARLY_POP 0
+#define CRB_EARLY_POP 1    // +0.7 % (profiles/r1g_sweeps.md section 6)
 #endif
 
 namespace crb

@@ -54,6 +54,33 @@ namespace crb
 
         __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
 
+        // k_shade's path record: all slot-indexed 16-byte loads issued together right after the queue entry is known.
+        // Written as `hit.w first, classify, then the rest`, the kernel ran a chain of five to six dependent DRAM round
+        // trips per tile (queue entry -> hit -> ray/throughput -> triangle -> material -> radiance; ncu: 49 % of DRAM
+        // peak at 31-43 % issue utilisation, stalls on exactly those first uses); the asm keeps ptxas from sinking the
+        // loads below the miss/hit branch. `rad` is only prefetched (it is consumed last; no registers held).
+#ifndef CRB_SHADE_GROUPED_LOADS
+#define CRB_SHADE_GROUPED_LOADS 1    // k_shade 14.5 -> 13.3 ms per 3 steps, +1.0 % end to end (profiles/r1g_sweeps.md section 6)
+#endif
+        __device__ __forceinline__ float4 ld128_grouped(const float4 *p)
+        {
+#if defined(CRB_EMU) || !CRB_SHADE_GROUPED_LOADS
+            return *p;
+#else
+            float4 v;
+            asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+            return v;
+#endif
+        }
+        __device__ __forceinline__ void prefetch_l2(const void *p)
+        {
+#if !defined(CRB_EMU) && CRB_SHADE_GROUPED_LOADS
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+            (void) p;
+#endif
+        }
+
         // ---- warp-aggregated queue push: one atomic per warp per queue
         __device__ __forceinline__ uint32_t warp_push(uint32_t *counter, bool pred)
         {
@@ -325,11 +352,13 @@ namespace crb
                     {
                         // unsorted mode: paths are shaded in queue (= screen) order
                         slot = ps.q_in[idx];
-                        cls  = __float_as_uint(ps.hit[slot].w) == INVALID_PRIM ? 0 : 1;
+                        cls  = -1;
                     }
-                    const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                    const float4 h4 = ld128_grouped(ps.hit + slot), ro = ld128_grouped(ps.ray_o + slot), rd = ld128_grouped(ps.ray_d + slot),
+                                 t4 = ld128_grouped(ps.thr + slot);
+                    prefetch_l2(ps.rad + slot);
+                    if (cls < 0) cls = __float_as_uint(h4.w) == INVALID_PRIM ? 0 : 1;
                     const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
-                    const float4 t4 = ps.thr[slot];
                     V3           thr = v3(t4.x, t4.y, t4.z);
                     const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
                     const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
@@ -355,7 +384,7 @@ namespace crb
                     else
                     {
                         const V3         dn  = normalize(d);
-                        const Surface    sf  = surface_at(sc, o, dn, ps.hit[slot]);
+                        const Surface    sf  = surface_at(sc, o, dn, h4);
                         const DMaterial  mat = sc.materials[sf.mat];
                         const float4     col = surface_colour(sc, mat, sf);
                         if (col.w == 0.0f)
@@ -514,11 +543,13 @@ namespace crb
                     else
                     {
                         slot = ps.q_in[idx];
-                        cls  = __float_as_uint(ps.hit[slot].w) == INVALID_PRIM ? 0 : 1;
+                        cls  = -1;
                     }
-                    const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                    const float4 h4 = ld128_grouped(ps.hit + slot), ro = ld128_grouped(ps.ray_o + slot), rd = ld128_grouped(ps.ray_d + slot),
+                                 t4 = ld128_grouped(ps.thr + slot);
+                    prefetch_l2(ps.rad + slot);
+                    if (cls < 0) cls = __float_as_uint(h4.w) == INVALID_PRIM ? 0 : 1;
                     const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
-                    const float4 t4 = ps.thr[slot];
                     const V3     thr = v3(t4.x, t4.y, t4.z);
                     const bool   specular = t4.w != 0.0f;
                     const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
@@ -553,7 +584,7 @@ namespace crb
                     }
                     else
                     {
-                        const Surface   sf  = surface_at(sc, o, dn, ps.hit[slot]);
+                        const Surface   sf  = surface_at(sc, o, dn, h4);
                         const DMaterial mat = sc.materials[sf.mat];
                         const float4    col = surface_colour(sc, mat, sf);
                         if (col.w == 0.0f)
