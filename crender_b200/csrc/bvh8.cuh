@@ -29,7 +29,7 @@
 #define CRB_TRI_BRANCHFREE 1    // +3.1 % (profiles/r1g_sweeps.md section 6)
 #endif
 #ifndef CRB_EARLY_POP
-#define CRB_EARLY_POP 1    // +0.7 % (profiles/r1g_sweeps.md section 6)
+#define CRB_EARLY_POP 2    // 1: +0.7 %, 2 (predicated in-place loads): +4.3 % (profiles/r1g_sweeps.md section 6)
 #endif
 
 namespace crb
@@ -386,7 +386,22 @@ namespace crb
                 // local-memory load is issued here and its latency hides behind the leaf phase (ncu: 20 % of k_trace's
                 // long-scoreboard stalls sat on a pop whose value the next instruction used). Visit order unchanged:
                 // the node phase runs only once tgroup is empty.
+#if CRB_EARLY_POP == 2 && !defined(CRB_EMU)
+                {
+                    // predicated local loads straight into group's registers: written in C++ (or as one 64-bit
+                    // load), ptxas loads into a temporary pair and moves it into `group` at once, i.e. waits for the
+                    // load right here; two 32-bit loads have no register-pair constraint and need no move
+                    const bool pop = active && (group.y & 0xff000000u) == 0u && sp > 0;
+                    sp -= pop ? 1 : 0;
+                    const size_t a = __cvta_generic_to_local(&stack[sp]);
+                    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.local.u32 %0, [%3];\n @p ld.local.u32 %1, [%3+4];\n}"
+                                 : "+r"(group.x), "+r"(group.y)
+                                 : "r"(unsigned(pop)), "l"(a)
+                                 : "memory");
+                }
+#else
                 if (active && (group.y & 0xff000000u) == 0u && sp > 0) group = stack[--sp];
+#endif
 #endif
                 // ---- leaf phase in lock step: ONE triangle per lane that has triangles waiting (an inner
                 // per-lane triangle loop was 52 % of k_trace's instructions at 2.7 active lanes; waiting for

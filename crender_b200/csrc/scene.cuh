@@ -16,7 +16,10 @@
 
 namespace crb
 {
-    struct DMaterial    // 48 bytes, 16-byte aligned rows
+#ifndef CRB_DMAT_ALIGN
+#define CRB_DMAT_ALIGN 16
+#endif
+    struct alignas(CRB_DMAT_ALIGN) DMaterial    // 48 bytes = three 16-byte vector loads (12 scalar loads without the alignment)
     {
         float    colour[4];
         uint32_t shade_type;
