@@ -361,6 +361,11 @@ def e2e(a, desc, scene_bytes, api, scenes, local):
     r = api.renderer(a.width, a.height, a.bounces, g, seed=0)
     r.render(spp)
     r.current_progress(out)
+    if not a.e2e_blocking_read:
+        # the asynchronous read path too: the first use of a second stream / copy engine in a process costs a one-off
+        # 1-140 ms of driver initialisation (seen on some boxes), which is not the product's time either
+        r.render(1, sync=False)
+        r.wait_read(r.current_progress_async(out))
     del r, g
     # two pinned host images: the read-back of step k (crb_render_read_async: snapshot after the step's kernels,
     # device->host on a second stream) overlaps the kernels of step k+1, like the reference's UI thread reading
@@ -373,9 +378,14 @@ def e2e(a, desc, scene_bytes, api, scenes, local):
     r = api.renderer(a.width, a.height, a.bounces, g, seed=0)
     t1 = time.perf_counter()
     marks, tickets = [], []
+    dbg = os.environ.get("CRB_BENCH_DEBUG")
     for k in range(a.steps):
+        ta = time.perf_counter()
         g.set_camera(desc.cam)  # the step's input
+        tb = time.perf_counter()
         r.render(spp, first_sample=k * spp, sync=False)
+        if dbg and k < 3:
+            sys.stderr.write("e2e step %d: set_camera %.2f ms, render() submit %.2f ms\n" % (k, (tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3))
         if a.e2e_blocking_read:
             r.current_progress(outs[k & 1])
         else:
