@@ -419,6 +419,8 @@ def e2e_multi(a, r, step, merged, barrier, torch, dist, world):
     stream = torch.cuda.ExternalStream(r.stream(), device=merged.device)
     copy_stream = torch.cuda.Stream(device=merged.device)
     done = [None, None]
+    with torch.cuda.stream(copy_stream):  # first use of the copy stream / engine is a one-off driver initialisation: not timed
+        hosts[1].copy_(bufs[1], non_blocking=True)
     barrier()
     q0 = r.current_stats().total_queries
     t0 = time.perf_counter()
