@@ -329,7 +329,11 @@ namespace crb
             return v3(cosf(phi) * sin_theta, cos_theta, sinf(phi) * sin_theta);
         }
 
-        __global__ void __launch_bounds__(256, 4) k_shade(DScene sc, RenderParams rp, PathState ps)
+        // CTA size of k_shade: its queue push is CTA-collective (three barriers per tile), so a CTA waits for its slowest warp
+#ifndef CRB_SHADE_BLOCK
+#define CRB_SHADE_BLOCK 128    // 256: 13.4, 128: 13.1, 512: 13.9 ms per 3 steps (profiles/r1g_sweeps.md section 6)
+#endif
+        __global__ void __launch_bounds__(CRB_SHADE_BLOCK, 1024 / CRB_SHADE_BLOCK) k_shade(DScene sc, RenderParams rp, PathState ps)
         {
             const uint32_t c0 = ps.counters[CTR_CLASS0], c1 = c0 + ps.counters[CTR_CLASS0 + 1], c2 = c1 + ps.counters[CTR_CLASS0 + 2],
                            n = ps.sorted ? c2 + ps.counters[CTR_CLASS0 + 3] : ps.counters[CTR_IN];
@@ -1079,9 +1083,10 @@ namespace crb
         const bool count = (flags & CRB_RENDER_FLAG_COUNTERS) != 0;
         static const int steps = getenv("CRB_TRACE_STEPS") ? atoi(getenv("CRB_TRACE_STEPS")) : TRACE_STEPS;    // tuning knob
 #ifdef CRB_EMU
-        const unsigned pgrid = 1, pblock = 1, tgrid = 1;
+        const unsigned pgrid = 1, pblock = 1, tgrid = 1, sgrid = 1, sblock = 1;
 #else
-        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC;
+        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC,
+                       sgrid = unsigned(n_sms) * (1024 / CRB_SHADE_BLOCK), sblock = CRB_SHADE_BLOCK;
         const Span span { take_event(), take_event() };
         CRB_CUDA_CHECK(cudaEventRecord(span.a, stream()));
 #endif
@@ -1123,7 +1128,7 @@ namespace crb
                 if (flags & CRB_RENDER_FLAG_EXTENDED)
                     CRB_LAUNCH(k_shade_ext, pgrid, pblock, st, dscene, rp, ps);
                 else
-                    CRB_LAUNCH(k_shade, pgrid, pblock, st, dscene, rp, ps);
+                    CRB_LAUNCH(k_shade, sgrid, sblock, st, dscene, rp, ps);
                 tock();
                 launches += ps.sorted ? 3 : 2;
                 if (dscene.sun.enabled || ((flags & CRB_RENDER_FLAG_EXTENDED) && dscene.n_lights))
