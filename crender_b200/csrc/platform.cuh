@@ -247,8 +247,13 @@ namespace crb
         std::multimap<std::pair<int, size_t>, void *>       free_blocks;    // (device, bytes) -> block
         std::unordered_map<void *, std::pair<int, size_t>>  live;           // blocks handed out that are cacheable
         size_t                                              cached = 0;
+        std::unordered_map<int, size_t>                     live_bytes;     // per device: bytes of the blocks in `live`
+        // per device: (total bytes, bytes held by anything that is not one of our blocks) as of the last driver query;
+        // dropped when an allocation fails
+        std::unordered_map<int, std::pair<size_t, size_t>>  budget;
         void trim_locked()
         {
+            budget.clear();
             int cur = 0;
             cudaGetDevice(&cur);
             for (auto &kv : free_blocks)
@@ -271,6 +276,35 @@ namespace crb
         DevBlockCache &c = dev_block_cache();
         std::lock_guard<std::mutex> lk(c.mu);
         return c.cached;
+    }
+    // Free device memory plus our recycled blocks on the current device, for planning. The driver is asked once per
+    // device (and again after a failed allocation): cudaMemGetInfo was measured at 0.1-34 ms per call on B200
+    // (profiles/r1k_submit_debug.txt), billed to the first render call of every new renderer. Afterwards the figure follows
+    // our own large blocks; memory taken by others in between shows up as a failed allocation, which re-asks.
+    inline size_t dev_available_bytes()
+    {
+        DevBlockCache &c = dev_block_cache();
+        int            dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        std::lock_guard<std::mutex> lk(c.mu);
+        const size_t                live = c.live_bytes[dev];
+        auto                        it = c.budget.find(dev);
+        if (it == c.budget.end())
+        {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+            {
+                cudaGetLastError();
+                return 0;
+            }
+            size_t cached_here = 0;
+            for (const auto &kv : c.free_blocks)
+                if (kv.first.first == dev) cached_here += kv.first.second;
+            const size_t used = total_b - free_b, ours = live + cached_here;
+            it = c.budget.insert({ dev, { total_b, used > ours ? used - ours : 0 } }).first;
+        }
+        const size_t total_b = it->second.first, foreign = it->second.second;
+        return total_b > foreign + live ? total_b - foreign - live : 0;
     }
 #endif
     inline void *dev_alloc(size_t bytes)
@@ -295,6 +329,7 @@ namespace crb
                 c.free_blocks.erase(it);
                 c.cached -= bytes;
                 c.live[p] = { dev, bytes };
+                c.live_bytes[dev] += bytes;
                 return p;
             }
         }
@@ -313,6 +348,7 @@ namespace crb
         {
             std::lock_guard<std::mutex> lk(c.mu);
             c.live[p] = { dev, bytes };
+            c.live_bytes[dev] += bytes;
         }
         return p;
 #endif
@@ -331,6 +367,7 @@ namespace crb
             {
                 const std::pair<int, size_t> key = it->second;
                 c.live.erase(it);
+                c.live_bytes[key.first] -= key.second;
                 if (c.cached + key.second <= DevBlockCache::MAX_CACHED)
                 {
                     // same guarantee as cudaFree: nothing on the device still uses the block when it is reused

@@ -23,6 +23,8 @@
 #include "render.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <vector>
 
 namespace crb
@@ -891,6 +893,10 @@ namespace crb
 #ifndef CRB_EMU
         CRB_CUDA_CHECK(cudaSetDevice(s->device));
         n_sms = s->n_sms;    // (cudaGetDeviceProperties costs tens of milliseconds; the scene already asked)
+        // experiment knob: keep the context's local-memory reservation at its high-water mark (the traversal stack lives in
+        // local memory; by default the driver may shrink the reservation when the device idles and re-grow it at a launch)
+        static const bool lmem_max = getenv("CRB_LMEM_MAX") && atoi(getenv("CRB_LMEM_MAX"));
+        if (lmem_max && cudaSetDeviceFlags(cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();
 #endif
         counters.alloc(CTR_COUNT);
         dstats.alloc(ST_COUNT);
@@ -1048,19 +1054,31 @@ namespace crb
         collect_time(false);
         const uint32_t nrows = row1 - row0;
         const uint32_t npix  = w * nrows;
+        // CRB_SUBMIT_DEBUG=1: host-clock breakdown of this call's submission on stderr (measurement hook)
+        static const bool submit_debug = getenv("CRB_SUBMIT_DEBUG") && atoi(getenv("CRB_SUBMIT_DEBUG"));
+        const auto        now          = [] { return std::chrono::steady_clock::now(); };
+        const auto        ms_since     = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+        const auto        t_enter      = now();
+        double            ms_meminfo = 0, ms_ensure = 0, ms_first_launch = 0;
         static const size_t tp_env = getenv("CRB_TARGET_PATHS") ? size_t(atoll(getenv("CRB_TARGET_PATHS"))) : 0;    // tuning knob
         size_t         tpaths    = tp_env ? tp_env : target_paths;
 #ifndef CRB_EMU
         {
             // never plan for more than a quarter of the free device memory (152 B of state per path)
-            size_t free_b = 0, total_b = 0;
-            if (capacity == 0 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) mem_path_cap = std::max<size_t>(size_t(1) << 20, (free_b + dev_cached_bytes()) / 4 / 152);
+            const auto t_a = now();
+            if (capacity == 0)
+                if (const size_t avail = dev_available_bytes()) mem_path_cap = std::max<size_t>(size_t(1) << 20, avail / 4 / 152);
             if (mem_path_cap) tpaths = std::min(tpaths, mem_path_cap);
+            ms_meminfo = ms_since(t_a);
         }
 #endif
         uint32_t       spp_batch = uint32_t(std::max<size_t>(1, tpaths / npix));
         spp_batch                = std::min(spp_batch, n);
-        ensure_paths(size_t(npix) * spp_batch);
+        {
+            const auto t_a = now();
+            ensure_paths(size_t(npix) * spp_batch);
+            ms_ensure = ms_since(t_a);
+        }
 
         PathState ps {};
         ps.ray_o = ray_o.p, ps.ray_d = ray_d.p, ps.thr = thr.p, ps.rad = rad.p, ps.hit = hit.p;
@@ -1104,7 +1122,9 @@ namespace crb
             CRB_LAUNCH(k_raygen, np, 1, st, dscene, rp, ps);
 #else
             tick(CRB_K_RAYGEN);
+            const auto t_a = now();
             CRB_LAUNCH(k_raygen, (np + 255) / 256, 256, st, dscene, rp, ps);
+            if (done == 0) ms_first_launch = ms_since(t_a);
             tock();
 #endif
             launches++;
@@ -1175,6 +1195,9 @@ namespace crb
         CRB_CUDA_CHECK(cudaEventRecord(span.b, stream()));
         spans.push_back(span);
 #endif
+        if (submit_debug)
+            fprintf(stderr, "crb submit: total %.2f ms (memory query %.2f, ensure_paths %.2f, first launch %.2f), first_sample %u\n", ms_since(t_enter), ms_meminfo,
+                    ms_ensure, ms_first_launch, first);
     }
 
     void Render::sync()
