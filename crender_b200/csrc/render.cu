@@ -83,17 +83,6 @@ namespace crb
 #endif
         }
 
-        // ---- warp-aggregated queue push: one atomic per warp per queue
-        __device__ __forceinline__ uint32_t warp_push(uint32_t *counter, bool pred)
-        {
-            const unsigned mask = __ballot_sync(0xffffffffu, pred);
-            if (mask == 0) return 0;
-            const int leader = __ffs(int(mask)) - 1;
-            uint32_t  base   = 0;
-            if (int(crb_lane_id()) == leader) base = atomicAdd(counter, uint32_t(__popc(mask)));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            return base + uint32_t(__popc(mask & ((1u << crb_lane_id()) - 1u)));
-        }
         // Block-aggregated reservation of queue space in NQ queues at once: warps count with a ballot, add
         // into shared memory, and ONE thread per queue issues the global atomic for the whole block
         // (same-address global atomics serialise in L2; per-warp pushes of a full-frame wavefront are
