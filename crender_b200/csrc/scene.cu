@@ -119,10 +119,10 @@ namespace crb
         if (!verts && ntris) throw Error(ERR_BUILD_VERTS, "add_mesh: null vertex buffer");
         HostModel m;
         m.ntris = ntris;
-        m.verts.assign(verts, verts + size_t(ntris) * 9);
-        if (uvs) m.uvs.assign(uvs, uvs + size_t(ntris) * 6);
+        host_copy(m.verts, verts, size_t(ntris) * 9);
+        if (uvs) host_copy(m.uvs, uvs, size_t(ntris) * 6);
         if (mat_idx)
-            m.mat_idx.assign(mat_idx, mat_idx + ntris);
+            host_copy(m.mat_idx, mat_idx, size_t(ntris));
         else
             m.mat_idx.assign(ntris, 0);
         uint32_t maxm = 0;

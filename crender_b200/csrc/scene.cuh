@@ -12,6 +12,11 @@
 #include "bvh_build.cuh"
 #include "platform.cuh"
 
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <utility>
 #include <vector>
 
 namespace crb
@@ -85,11 +90,99 @@ namespace crb
         DCamera         cam;
     };
 
+    // Host copy of the caller's arrays (the library copies at add_mesh so the caller may free them, SURVEY.md 8b "Ownership").
+    // The copy of a large mesh is bound by the first touch of fresh pages, not by memcpy (36 MB: 28 ms into fresh pages,
+    // 7 ms into touched ones on the development host; touching from 4 threads was 4x SLOWER there, so no threads), and an
+    // interactive host loads and drops models repeatedly. So: resize() does not zero-fill first (default-initialising
+    // construct), and large blocks are recycled through a bounded, exact-size free list instead of going back to the OS.
+    struct HostBlockCache
+    {
+        static constexpr size_t         MIN_BLOCK = size_t(1) << 20, MAX_CACHED = size_t(1) << 30;
+        std::mutex                      mu;
+        std::multimap<size_t, void *>   free_blocks;
+        size_t                          cached = 0;
+    };
+    inline HostBlockCache &host_block_cache()
+    {
+        static HostBlockCache *c = new HostBlockCache;    // never destroyed: scenes may outlive static destruction
+        return *c;
+    }
+    template<class T>
+    struct NoInitAlloc
+    {
+        using value_type = T;
+        NoInitAlloc() = default;
+        template<class U>
+        NoInitAlloc(const NoInitAlloc<U> &)
+        {
+        }
+        T *allocate(size_t n)
+        {
+            const size_t bytes = n * sizeof(T);
+            if (bytes >= HostBlockCache::MIN_BLOCK)
+            {
+                HostBlockCache             &c = host_block_cache();
+                std::lock_guard<std::mutex> lk(c.mu);
+                auto                        it = c.free_blocks.find(bytes);
+                if (it != c.free_blocks.end())
+                {
+                    void *p = it->second;
+                    c.free_blocks.erase(it);
+                    c.cached -= bytes;
+                    return static_cast<T *>(p);
+                }
+            }
+            return static_cast<T *>(::operator new(bytes));
+        }
+        void deallocate(T *p, size_t n)
+        {
+            const size_t bytes = n * sizeof(T);
+            if (bytes >= HostBlockCache::MIN_BLOCK)
+            {
+                HostBlockCache             &c = host_block_cache();
+                std::lock_guard<std::mutex> lk(c.mu);
+                if (c.cached + bytes <= HostBlockCache::MAX_CACHED)
+                {
+                    c.free_blocks.insert({ bytes, p });
+                    c.cached += bytes;
+                    return;
+                }
+            }
+            ::operator delete(p);
+        }
+        template<class U, class... A>
+        void construct(U *p, A &&...a)
+        {
+            if constexpr (sizeof...(A) == 0)
+                ::new (static_cast<void *>(p)) U;    // default-initialised: trivial types stay untouched
+            else
+                ::new (static_cast<void *>(p)) U(std::forward<A>(a)...);
+        }
+        template<class U>
+        bool operator==(const NoInitAlloc<U> &) const
+        {
+            return true;
+        }
+        template<class U>
+        bool operator!=(const NoInitAlloc<U> &) const
+        {
+            return false;
+        }
+    };
+    template<class T>
+    using HostVec = std::vector<T, NoInitAlloc<T>>;
+    template<class T>
+    inline void host_copy(HostVec<T> &dst, const T *src, size_t n)
+    {
+        dst.resize(n);
+        if (n) memcpy(dst.data(), src, n * sizeof(T));
+    }
+
     struct HostModel
     {
         uint32_t                  ntris = 0;
-        std::vector<float>        verts, uvs;
-        std::vector<uint32_t>     mat_idx;
+        HostVec<float>            verts, uvs;
+        HostVec<uint32_t>         mat_idx;
         std::vector<crb_material> materials;
         std::vector<float>        transforms;    // 16 floats each, column-major
     };

@@ -525,3 +525,25 @@ def check_recycled_memory_is_clean(lib_path):
     a1 = run(scenes.terrain_city(24, 2, n_buildings=12), 1)
     for x, y in zip(a0, a1):
         np.testing.assert_array_equal(x, y)
+
+    # the host copies of the caller's arrays are recycled too (scene.cuh HostBlockCache, blocks of 1 MB and more):
+    # a scene that inherits the blocks of a destroyed one of the same size must see only its own geometry
+    def hits(desc, rays):
+        g = api.scene(lib_path=lib_path)
+        scenes.load(desc, g)
+        g.commit()
+        h = g.cast_rays(rays).copy()
+        g.close()
+        return h
+
+    da, db = scenes.mesh_scene(200, 80, seed=1), scenes.mesh_scene(200, 80, seed=5)  # 32000 triangles: 1.15 MB of vertices each
+    assert da.meshes[0].verts.nbytes >= 1 << 20 and da.meshes[0].verts.shape == db.meshes[0].verts.shape
+    lo, hi = da.aabb()
+    rays = scenes.random_rays(lo, hi, 4000, seed=9)
+    h0 = hits(da, rays)
+    h1 = hits(db, rays)
+    h2 = hits(da, rays)
+    for k in ("t", "prim", "model", "inst"):
+        np.testing.assert_array_equal(h0[k], h2[k])
+    assert (h0["prim"] != h1["prim"]).any()  # the second scene really was different
+
