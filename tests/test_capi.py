@@ -23,6 +23,13 @@ def test_header_and_binding_table_agree():
     assert declared_functions() == sorted(_capi.SIGNATURES)
 
 
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md maps each reference interface to the entry point that replaces it: none may be left out."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_functions() if n not in doc]
+    assert not missing, missing
+
+
 def test_library_exports_every_declared_symbol(product_lib):
     lib = _capi.load(product_lib)
     for name in declared_functions():
