@@ -25,6 +25,8 @@ METAL, SMOOTH, GLASS = 0, 1, 2  # cr::material::type
 PERSPECTIVE, ORTHOGRAPHIC = 0, 1  # cr::camera::mode
 RAW_SUM, PROGRESS, ALBEDO, NORMAL, DEPTH = 0, 1, 2, 3, 4
 K_RAYGEN, K_TRACE, K_SHADE, K_SHADOW, K_ADVANCE, K_ACCUMULATE = range(6)  # crb_stats.kernel_ms index
+PARTITION_SPP, PARTITION_TILE = 0, 1  # multi-GPU work split (BASELINE configs 4 / 5)
+MERGE_NONE, MERGE_PEER_KERNEL, MERGE_NCCL = 0, 1, 2
 
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmin", "<f4"), ("d", "<f4", 3), ("tmax", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("model", "<u4"), ("inst", "<u4")])
@@ -257,11 +259,24 @@ class renderer:
     management thread issues them in a loop until the target spp, renderer.cpp:116-144)."""
 
     def __init__(self, res_x: int, res_y: int, bounces: int, scn: scene, seed: int = 0, counters: bool = False, timers: bool = False,
-                 material_sort: bool = False, extended: bool = False):
+                 material_sort: bool = False, extended: bool = False, gpus=None, partition: int = PARTITION_SPP, comm=None):
+        """gpus: None = the scene's GPU; an int N or a list of device ids = one process driving N GPUs
+        (crb_render_create_multi: the library replicates the scene and merges the accumulators itself).
+        comm = (nccl_id_bytes, rank, nranks): one process per GPU (crb_render_create_rank)."""
         self._lib = scn._lib
         self._scene = scn
         h = C.c_void_p()
-        _capi.check(self._lib, self._lib.crb_render_create(scn._h, res_x, res_y, bounces, seed, (1 if counters else 0) | (2 if timers else 0) | (4 if material_sort else 0) | (8 if extended else 0), C.byref(h)))
+        flags = (1 if counters else 0) | (2 if timers else 0) | (4 if material_sort else 0) | (8 if extended else 0)
+        if comm is not None:
+            ident, rank, nranks = comm
+            buf = C.create_string_buffer(bytes(ident), 128) if ident is not None else None
+            _capi.check(self._lib, self._lib.crb_render_create_rank(scn._h, buf, rank, nranks, partition, res_x, res_y, bounces, seed, flags, C.byref(h)))
+        elif gpus is not None:
+            devs = list(range(gpus)) if isinstance(gpus, int) else [int(d) for d in gpus]
+            arr = (C.c_int * len(devs))(*devs)
+            _capi.check(self._lib, self._lib.crb_render_create_multi(scn._h, arr, len(devs), partition, res_x, res_y, bounces, seed, flags, C.byref(h)))
+        else:
+            _capi.check(self._lib, self._lib.crb_render_create(scn._h, res_x, res_y, bounces, seed, flags, C.byref(h)))
         self._h = h
         self._res = (res_x, res_y)
         self._spp_target = 0
@@ -311,6 +326,19 @@ class renderer:
 
     def set_rows(self, y0: int, y1: int):
         _capi.check(self._lib, self._lib.crb_render_set_rows(self._h, y0, y1))
+
+    def set_bands(self, band_rows: int, first: int, stride: int):
+        """Interleaved row bands first, first+stride, ... of band_rows rows each, rendered as one launch sequence."""
+        _capi.check(self._lib, self._lib.crb_render_set_bands(self._h, band_rows, first, stride))
+
+    def flush(self):
+        """Multi-GPU handles: start merging the accumulators now (asynchronous; the read calls imply it)."""
+        _capi.check(self._lib, self._lib.crb_render_flush(self._h))
+
+    def info(self) -> dict:
+        a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        _capi.check(self._lib, self._lib.crb_render_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"gpus_local": a.value, "ranks": b.value, "partition": ("spp", "tile")[c.value], "merge": ("none", "peer-kernel", "nccl")[d.value]}
 
     # ---- rendering
     def render(self, n_spp: int, first_sample: Optional[int] = None, sync: bool = True):

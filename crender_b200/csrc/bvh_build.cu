@@ -270,6 +270,7 @@ namespace crb
             float          *sah;         // accumulated wide-tree SAH cost (area-weighted), informational
             float           root_area;
             int             use_dp;
+            uint32_t        max_nodes;   // capacity of the node pool and of both collapse queues; overflow sets counters[7]
         };
 
         __device__ __forceinline__ int ref_count(const BinTree &t, int ref) { return ref < 0 ? 1 : t.count[ref]; }
@@ -399,6 +400,14 @@ namespace crb
             const uint32_t child_base = n_inner ? atomicAdd(c.counters + 0, uint32_t(n_inner)) : 0u;
             const uint32_t tri_base   = n_ltris ? atomicAdd(c.counters + 1, uint32_t(n_ltris)) : 0u;
             const uint32_t out_base   = n_inner ? atomicAdd(c.counters + 2, uint32_t(n_inner)) : 0u;
+            // n/2+8 nodes hold for the greedy collapse (a non-full node has only leaf children); the DP collapse can
+            // plateau (C(m,j) == C(m,j-1)) and emit thinner nodes. Never write past the pool / queues: flag, and the
+            // host rebuilds this stage with the true bound (every wide inner node consumes a binary inner node: <= n)
+            if (n_inner && (child_base + uint32_t(n_inner) > c.max_nodes || out_base + uint32_t(n_inner) > c.max_nodes))
+            {
+                atomicOr(c.counters + 7, 1u);
+                return;
+            }
 
             // quantisation frame (double: the grid must contain every child box exactly-conservatively)
             unsigned eb[3];
@@ -550,7 +559,7 @@ namespace crb
         t.flags      = carve<int>(p, ni);
         t.dpc        = carve<float>(p, ni * 7);
         t.dpk        = carve<unsigned char>(p, ni * 8);
-        uint2    *q0 = carve<uint2>(p, max_nodes), *q1 = carve<uint2>(p, max_nodes);
+        uint2    *q0_small = carve<uint2>(p, max_nodes), *q1_small = carve<uint2>(p, max_nodes);
         uint32_t *counters = carve<uint32_t>(p, 8);
 #ifndef CRB_EMU
         uint32_t *rs_hist = carve<uint32_t>(p, radix_sort_hist_entries(n));
@@ -616,35 +625,55 @@ namespace crb
         }
 
         // ---- K4
-        {
-            uint32_t init[8] = { 1, 0, 0, 0, 0, 0, 0, 0 };    // node 0 = root is pre-allocated
-            dev_upload(counters, init, sizeof(init), stream);
-            uint2 first = make_uint2(unsigned(root_ref), 0u);
-            dev_upload(q0, &first, sizeof(first), stream);
-        }
-        CollapseCtx c;
-        c.t = t, c.plo = plo, c.phi = phi, c.vals = vals, c.wv = d_wverts, c.nodes = nodes.p, c.tris = tris.p;
-        c.counters = counters, c.sah = reinterpret_cast<float *>(counters + 4), c.root_area = root_area;
-        c.use_dp = (opt.optimal_collapse && n > 1) ? 1 : 0;
-        if (c.use_dp)
-        {
-            dev_zero(t.flags, ni * sizeof(int), stream);
-            CRB_LAUNCH(k_collapse_dp, gn, B, stream, int(n), t, plo, phi, vals, opt.cost_prim);
-        }
-        uint32_t n_in  = 1;
+        size_t   pool_nodes = max_nodes;
+        uint2   *q0 = q0_small, *q1 = q1_small;
+        DBuf<uint2> q_big;
         uint32_t depth = 0;
-        uint2   *qin = q0, *qout = q1;
-        while (n_in)
+        for (int attempt = 0;; attempt++)
         {
-            depth++;
-            CRB_LAUNCH(k_collapse, (n_in + 127) / 128, 128, stream, c, qin, n_in, qout);
-            uint32_t cnt[3];
-            dev_download(cnt, counters, sizeof(cnt), stream);
-            if (cnt[0] > max_nodes) throw Error(ERR_GENERIC, "internal: wide node pool overflow");
-            n_in = cnt[2];
-            const uint32_t zero = 0;
-            dev_upload(counters + 2, &zero, 4, stream);
-            std::swap(qin, qout);
+            {
+                uint32_t init[8] = { 1, 0, 0, 0, 0, 0, 0, 0 };    // node 0 = root is pre-allocated
+                dev_upload(counters, init, sizeof(init), stream);
+                uint2 first = make_uint2(unsigned(root_ref), 0u);
+                dev_upload(q0, &first, sizeof(first), stream);
+            }
+            CollapseCtx c;
+            c.t = t, c.plo = plo, c.phi = phi, c.vals = vals, c.wv = d_wverts, c.nodes = nodes.p, c.tris = tris.p;
+            c.counters = counters, c.sah = reinterpret_cast<float *>(counters + 4), c.root_area = root_area;
+            c.use_dp    = (opt.optimal_collapse && n > 1) ? 1 : 0;
+            c.max_nodes = uint32_t(pool_nodes);
+            if (c.use_dp && attempt == 0)
+            {
+                dev_zero(t.flags, ni * sizeof(int), stream);
+                CRB_LAUNCH(k_collapse_dp, gn, B, stream, int(n), t, plo, phi, vals, opt.cost_prim);
+            }
+            uint32_t n_in = 1;
+            bool     overflow = false;
+            uint2   *qin = q0, *qout = q1;
+            depth = 0;
+            while (n_in)
+            {
+                depth++;
+                CRB_LAUNCH(k_collapse, (n_in + 127) / 128, 128, stream, c, qin, n_in, qout);
+                uint32_t cnt[8];
+                dev_download(cnt, counters, sizeof(cnt), stream);
+                if (cnt[7] || cnt[0] > pool_nodes)
+                {
+                    overflow = true;
+                    break;
+                }
+                n_in = cnt[2];
+                const uint32_t zero = 0;
+                dev_upload(counters + 2, &zero, 4, stream);
+                std::swap(qin, qout);
+            }
+            if (!overflow) break;
+            if (attempt > 0) throw Error(ERR_GENERIC, "internal: wide node pool overflow");
+            // the true bound: every wide inner node consumes at least one binary inner node
+            pool_nodes = size_t(n) + 8;
+            nodes.alloc(pool_nodes * 5);
+            q_big.alloc(pool_nodes * 2);
+            q0 = q_big.p, q1 = q_big.p + pool_nodes;
         }
         uint32_t fin[5];
         dev_download(fin, counters, sizeof(fin), stream);

@@ -1,10 +1,15 @@
 // capi.cu — the extern "C" boundary declared in include/crender_b200.h.
 // Exceptions never cross the boundary: every entry point returns a crb_status and records the
 // message for crb_last_error(). (The reference terminates the process instead: util/exception.h:9-13.)
+// Every entry point that takes a handle runs under the handle's CUDA device (DeviceScope) and restores the
+// caller's current device on return, so scenes on different GPUs can be driven from one host thread and a host
+// whose other libraries switch devices (torch) cannot make the library allocate or launch on a foreign GPU.
 #include "../../include/crender_b200.h"
+#include "multi.cuh"
 #include "render.cuh"
 #include "scene.cuh"
 
+#include <memory>
 #include <new>
 #include <string>
 
@@ -12,10 +17,13 @@ struct crb_scene
 {
     crb::Scene s;
 };
+// one handle type for the single-GPU renderer and the multi-GPU one (crb_render_create_multi / _rank)
 struct crb_render
 {
-    crb::Render r;
-    crb_render(crb::Scene *s, uint32_t w, uint32_t h, uint32_t mb, uint32_t seed, uint32_t flags) : r(s, w, h, mb, seed, flags) {}
+    std::unique_ptr<crb::Render>      r;
+    std::unique_ptr<crb::MultiRender> m;
+    crb::Scene                       *scene = nullptr;
+    int device() const { return scene->device; }
 };
 
 namespace
@@ -49,6 +57,29 @@ namespace
     void need(const void *p, const char *what)
     {
         if (!p) throw crb::Error(crb::ERR_INVALID_ARG, std::string("null argument: ") + what);
+    }
+    // entry points on a scene / renderer handle: null check + the handle's device
+    template<typename F>
+    int on_scene(crb_scene *s, F f)
+    {
+        return guarded([&] {
+            need(s, "scene");
+            crb::DeviceScope ds(s->s.device);
+            f(s->s);
+        });
+    }
+    template<typename F>
+    int on_render(crb_render *r, F f)
+    {
+        return guarded([&] {
+            need(r, "render");
+            crb::DeviceScope ds(r->device());
+            f(*r);
+        });
+    }
+    void single_only(crb_render &h, const char *what)
+    {
+        if (h.m) throw crb::Error(crb::ERR_INVALID_ARG, std::string(what) + ": not available on a multi-GPU handle (the partition owns the rows / buffers)");
     }
 }    // namespace
 
@@ -97,42 +128,41 @@ int crb_scene_create(crb_scene **out)
 }
 int crb_scene_destroy(crb_scene *s)
 {
-    return guarded([&] { delete s; });
+    return guarded([&] {
+        if (!s) return;
+        crb::DeviceScope ds(s->s.device);
+        delete s;
+    });
 }
 int crb_scene_add_mesh(crb_scene *s, const float *verts, const float *uvs, const uint32_t *mat_idx, uint32_t ntris, int *model_id)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         const int id = s->s.add_mesh(verts, uvs, mat_idx, ntris);
         if (model_id) *model_id = id;
     });
 }
 int crb_scene_set_materials(crb_scene *s, int model, const crb_material *m, uint32_t n)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         s->s.set_materials(model, m, n);
     });
 }
 int crb_scene_set_instances(crb_scene *s, int model, const float *mats, uint32_t n)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         s->s.set_instances(model, mats, n);
     });
 }
 int crb_scene_add_texture(crb_scene *s, const float *rgba, uint32_t w, uint32_t h, int *tex_id)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         const int id = s->s.add_texture(rgba, w, h);
         if (tex_id) *tex_id = id;
     });
 }
 int crb_scene_set_sun(crb_scene *s, const crb_sun *sun, int enabled)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         if (sun) s->s.sun = *sun;
         s->s.sun_enabled = enabled != 0;
         s->s.version++;
@@ -140,25 +170,24 @@ int crb_scene_set_sun(crb_scene *s, const crb_sun *sun, int enabled)
 }
 int crb_scene_set_skybox(crb_scene *s, const float *rgba, uint32_t w, uint32_t h, float ru, float rv)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         crb::Scene &S = s->s;
         if (rgba && w && h)
         {
             S.skybox.assign(rgba, rgba + size_t(w) * h * 4);
             S.sky_w = w, S.sky_h = h;
+            S.sky_version++;
             S.upload_skybox();
         }
         else
-            S.sky_w = S.sky_h = 0;
+            S.sky_w = S.sky_h = 0, S.sky_version++;
         S.sky_rot[0] = ru, S.sky_rot[1] = rv;
         S.version++;
     });
 }
 int crb_scene_set_camera(crb_scene *s, const crb_camera *c)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         need(c, "camera");
         if (c->mode > 1) throw crb::Error(crb::ERR_INVALID_ARG, "camera mode must be 0 (perspective) or 1 (orthographic)");
         s->s.camera = *c;
@@ -167,8 +196,7 @@ int crb_scene_set_camera(crb_scene *s, const crb_camera *c)
 }
 int crb_scene_commit(crb_scene *s, crb_build_info *info)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         s->s.commit();
         if (info)
         {
@@ -186,45 +214,39 @@ int crb_scene_commit(crb_scene *s, crb_build_info *info)
 
 int crb_intersect_batch(crb_scene *s, const crb_ray *rays, crb_hit *hits, uint64_t n, int on_device)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         crb::intersect_batch(s->s, rays, hits, n, on_device != 0);
     });
 }
 int crb_occluded_batch(crb_scene *s, const crb_ray *rays, uint8_t *occ, uint64_t n, int on_device)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         crb::occluded_batch(s->s, rays, occ, n, on_device != 0);
     });
 }
 int crb_trace_counters(crb_scene *s, const crb_ray *rays, uint64_t n, int on_device, int any_hit, uint64_t *nodes, uint64_t *tris)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         crb::trace_counters(s->s, rays, n, on_device != 0, any_hit != 0, nodes, tris);
     });
 }
 int crb_microbench_read(crb_scene *s, uint64_t bytes, int iters, double *gb_per_s)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         need(gb_per_s, "gb_per_s");
         *gb_per_s = crb::read_bandwidth_gbs(s->s, size_t(bytes), iters);
     });
 }
 int crb_last_query_ms(crb_scene *s, double *ms)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         need(ms, "ms");
         *ms = s->s.last_query_ms;
     });
 }
 int crb_scene_stream(crb_scene *s, void **stream)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         need(stream, "stream");
         *stream = (void *) s->s.stream;
     });
@@ -232,8 +254,7 @@ int crb_scene_stream(crb_scene *s, void **stream)
 
 int crb_post_process(crb_scene *s, const float *rgba, uint32_t w, uint32_t h, const crb_post_settings *ps, float *out)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &) {
         need(rgba, "rgba_host");
         need(ps, "settings");
         need(out, "out_host");
@@ -247,148 +268,191 @@ int crb_post_process(crb_scene *s, const float *rgba, uint32_t w, uint32_t h, co
 }
 int crb_render_post_process(crb_render *r, const crb_post_settings *ps, float *out)
 {
-    return guarded([&] {
-        need(r, "render");
+    return on_render(r, [&](crb_render &h) {
         need(ps, "settings");
         need(out, "out_host");
-        r->r.sync();
-        crb::post_process(*r->r.scene, r->r.display.p, r->r.w, r->r.h, *ps, out);
+        if (h.m)
+        {
+            const float4 *src = h.m->merged_buffer(CRB_PROGRESS);
+            h.m->sync();
+            crb::post_process(*h.scene, src, h.m->w, h.m->h, *ps, out);
+            return;
+        }
+        h.r->sync();
+        crb::post_process(*h.scene, h.r->display.p, h.r->w, h.r->h, *ps, out);
     });
 }
 
 // ------------------------------------------------------------------ renderer
 int crb_render_create(crb_scene *s, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed, uint32_t flags, crb_render **out)
 {
-    return guarded([&] {
-        need(s, "scene");
+    return on_scene(s, [&](crb::Scene &sc) {
         need(out, "out");
         if (!w || !h) throw crb::Error(crb::ERR_INVALID_ARG, "render target must be non-empty");
-        *out = new crb_render(&s->s, w, h, max_bounces, seed, flags);
+        auto hdl   = std::make_unique<crb_render>();
+        hdl->scene = &sc;
+        hdl->r     = std::make_unique<crb::Render>(&sc, w, h, max_bounces, seed, flags);
+        *out       = hdl.release();
+    });
+}
+int crb_render_create_multi(crb_scene *s, const int *devices, int ngpus, int partition, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t seed,
+                            uint32_t flags, crb_render **out)
+{
+    return on_scene(s, [&](crb::Scene &sc) {
+        need(out, "out");
+        if (!w || !h) throw crb::Error(crb::ERR_INVALID_ARG, "render target must be non-empty");
+        auto hdl   = std::make_unique<crb_render>();
+        hdl->scene = &sc;
+        hdl->m     = std::make_unique<crb::MultiRender>(&sc, devices, ngpus, partition, w, h, max_bounces, seed, flags);
+        *out       = hdl.release();
+    });
+}
+int crb_comm_unique_id(void *id128)
+{
+    return guarded([&] {
+        need(id128, "id128");
+        crb::nccl_unique_id(id128);
+    });
+}
+int crb_render_create_rank(crb_scene *s, const void *id128, int rank, int nranks, int partition, uint32_t w, uint32_t h, uint32_t max_bounces,
+                           uint32_t seed, uint32_t flags, crb_render **out)
+{
+    return on_scene(s, [&](crb::Scene &sc) {
+        need(out, "out");
+        if (!w || !h) throw crb::Error(crb::ERR_INVALID_ARG, "render target must be non-empty");
+        auto hdl   = std::make_unique<crb_render>();
+        hdl->scene = &sc;
+        hdl->m     = std::make_unique<crb::MultiRender>(&sc, id128, rank, nranks, partition, w, h, max_bounces, seed, flags);
+        *out       = hdl.release();
+    });
+}
+int crb_render_info(crb_render *r, int *ngpus_local, int *nranks, int *partition, int *merge_kind)
+{
+    return on_render(r, [&](crb_render &h) {
+        if (ngpus_local) *ngpus_local = h.m ? int(h.m->locals.size()) : 1;
+        if (nranks) *nranks = h.m ? h.m->world : 1;
+        if (partition) *partition = h.m ? h.m->partition : CRB_PARTITION_SPP;
+        if (merge_kind) *merge_kind = !h.m || h.m->world == 1 ? CRB_MERGE_NONE : (h.m->fused_peers ? CRB_MERGE_PEER_KERNEL : CRB_MERGE_NCCL);
     });
 }
 int crb_render_destroy(crb_render *r)
 {
-    return guarded([&] { delete r; });
+    return guarded([&] {
+        if (!r) return;
+        crb::DeviceScope ds(r->device());
+        delete r;
+    });
 }
 int crb_render_reset(crb_render *r)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.reset();
-    });
+    return on_render(r, [&](crb_render &h) { h.m ? h.m->reset() : h.r->reset(); });
 }
-int crb_render_set_resolution(crb_render *r, uint32_t w, uint32_t h)
+int crb_render_set_resolution(crb_render *r, uint32_t w, uint32_t hh)
 {
-    return guarded([&] {
-        need(r, "render");
-        if (!w || !h) throw crb::Error(crb::ERR_INVALID_ARG, "render target must be non-empty");
-        r->r.set_resolution(w, h);
+    return on_render(r, [&](crb_render &h) {
+        if (!w || !hh) throw crb::Error(crb::ERR_INVALID_ARG, "render target must be non-empty");
+        h.m ? h.m->set_resolution(w, hh) : h.r->set_resolution(w, hh);
     });
 }
 int crb_render_set_max_bounces(crb_render *r, uint32_t b)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.max_bounces = b;
+    return on_render(r, [&](crb_render &h) {
+        if (h.m)
+            h.m->set_max_bounces(b);
+        else
+            h.r->max_bounces = b;
     });
 }
 int crb_render_refresh(crb_render *r)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.refresh();
-    });
+    return on_render(r, [&](crb_render &h) { h.m ? h.m->refresh() : h.r->refresh(); });
 }
 int crb_render_set_rows(crb_render *r, uint32_t y0, uint32_t y1)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.set_rows(y0, y1);
+    return on_render(r, [&](crb_render &h) {
+        single_only(h, "crb_render_set_rows");
+        h.r->set_rows(y0, y1);
+    });
+}
+int crb_render_set_bands(crb_render *r, uint32_t band_rows, uint32_t first, uint32_t stride)
+{
+    return on_render(r, [&](crb_render &h) {
+        single_only(h, "crb_render_set_bands");
+        h.r->set_bands(band_rows, first, stride);
     });
 }
 int crb_render_samples(crb_render *r, uint32_t first, uint32_t n)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.render_samples(first, n);
+    return on_render(r, [&](crb_render &h) { h.m ? h.m->render_samples(first, n) : h.r->render_samples(first, n); });
+}
+int crb_render_flush(crb_render *r)
+{
+    return on_render(r, [&](crb_render &h) {
+        if (h.m) h.m->flush();
     });
 }
 int crb_render_sync(crb_render *r)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.sync();
-    });
+    return on_render(r, [&](crb_render &h) { h.m ? h.m->sync() : h.r->sync(); });
 }
 int crb_render_read(crb_render *r, int kind, float *dst)
 {
-    return guarded([&] {
-        need(r, "render");
+    return on_render(r, [&](crb_render &h) {
         need(dst, "dst");
-        r->r.read(kind, dst);
+        h.m ? h.m->read(kind, dst) : h.r->read(kind, dst);
     });
 }
 int crb_render_read_async(crb_render *r, int kind, float *dst, uint64_t *ticket)
 {
-    return guarded([&] {
-        need(r, "render");
+    return on_render(r, [&](crb_render &h) {
         need(dst, "dst");
         need(ticket, "ticket");
-        *ticket = r->r.read_async(kind, dst);
+        *ticket = h.m ? h.m->read_async(kind, dst) : h.r->read_async(kind, dst);
     });
 }
 int crb_render_read_wait(crb_render *r, uint64_t ticket)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.read_wait(ticket);
-    });
+    return on_render(r, [&](crb_render &h) { h.m ? h.m->read_wait(ticket) : h.r->read_wait(ticket); });
 }
 int crb_render_stats(crb_render *r, crb_stats *out)
 {
-    return guarded([&] {
-        need(r, "render");
+    return on_render(r, [&](crb_render &h) {
         need(out, "out");
-        r->r.stats(*out);
+        h.m ? h.m->stats(*out) : h.r->stats(*out);
     });
 }
 int crb_render_restore(crb_render *r, const float *raw, uint32_t passes)
 {
-    return guarded([&] {
-        need(r, "render");
+    return on_render(r, [&](crb_render &h) {
         need(raw, "raw_sum_rgba_host");
-        r->r.restore(raw, passes);
+        h.m ? h.m->restore(raw, passes) : h.r->restore(raw, passes);
     });
 }
 int crb_render_accum_ptr(crb_render *r, void **p, uint64_t *n)
 {
-    return guarded([&] {
-        need(r, "render");
+    return on_render(r, [&](crb_render &h) {
         need(p, "device_ptr");
-        *p = r->r.accum.p;
-        if (n) *n = uint64_t(r->r.w) * r->r.h * 4;
+        crb::Render &R = h.m ? *h.m->root().render : *h.r;    // multi handle: the first local rank's own accumulator
+        *p             = R.accum.p;
+        if (n) *n = uint64_t(R.w) * R.h * 4;
     });
 }
 int crb_render_set_pass_count(crb_render *r, uint32_t passes)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.passes = passes;
+    return on_render(r, [&](crb_render &h) {
+        single_only(h, "crb_render_set_pass_count");
+        h.r->set_pass_count(passes);
     });
 }
 int crb_render_resolve(crb_render *r)
 {
-    return guarded([&] {
-        need(r, "render");
-        r->r.resolve();
-    });
+    return on_render(r, [&](crb_render &h) { h.m ? h.m->resolve() : h.r->resolve(); });
 }
 int crb_render_stream(crb_render *r, void **stream)
 {
-    return guarded([&] {
-        need(r, "render");
+    return on_render(r, [&](crb_render &h) {
         need(stream, "stream");
-        *stream = (void *) r->r.stream();
+        *stream = (void *) (h.m ? h.m->root().render->stream() : h.r->stream());
     });
 }
 }

@@ -38,6 +38,7 @@ namespace crb
         ERR_NO_DEVICE   = 10,
         ERR_CUDA        = 11,
         ERR_OOM         = 12,
+        ERR_NCCL        = 13,
         ERR_BUILD_VERTS = 30,    // data/errors.json "30" (vertex buffer)
         ERR_BUILD_INDEX = 31,    // data/errors.json "31" (index buffer)
         ERR_BVH_DEPTH   = 32,
@@ -234,6 +235,33 @@ __device__ __forceinline__ unsigned crb_lane_id()
 
 namespace crb
 {
+    // Makes `dev` the calling thread's current CUDA device for the lifetime of the object and restores the previous one:
+    // every C-ABI entry point that takes a handle runs under the handle's device, whatever the host thread (or another
+    // library in the process, e.g. torch) had selected.
+    struct DeviceScope
+    {
+#ifndef CRB_EMU
+        int  prev = -1;
+        bool changed = false;
+        explicit DeviceScope(int dev)
+        {
+            if (cudaGetDevice(&prev) == cudaSuccess && prev != dev)
+            {
+                CRB_CUDA_CHECK(cudaSetDevice(dev));
+                changed = true;
+            }
+        }
+        ~DeviceScope()
+        {
+            if (changed) cudaSetDevice(prev);
+        }
+#else
+        explicit DeviceScope(int) {}
+#endif
+        DeviceScope(const DeviceScope &)            = delete;
+        DeviceScope &operator=(const DeviceScope &) = delete;
+    };
+
     // ---- device memory helpers (cudaMalloc on the product; malloc in the test harness)
 #ifndef CRB_EMU
     // Large device blocks are recycled instead of going back to the driver: cudaFree / cudaMalloc of the

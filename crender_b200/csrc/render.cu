@@ -140,6 +140,16 @@ namespace crb
 
         __device__ __forceinline__ uint32_t src_tri(const DScene &sc, uint32_t flat) { return sc.flat_src ? __ldg(sc.flat_src + flat) : flat; }
 
+        // local row r of this render call -> frame row y in sample space: a contiguous range [row0, row0+nrows), or the
+        // interleaved bands of the tile partition (band rows each, every band_stride-th band starting at band_first):
+        // all of a GPU's bands are one launch sequence, not one per band
+        __device__ __forceinline__ uint32_t row_of(const RenderParams &rp, uint32_t r)
+        {
+            if (rp.band == 0) return rp.row0 + r;
+            const uint32_t b = r / rp.band;
+            return (b * rp.band_stride + rp.band_first) * rp.band + (r - b * rp.band);
+        }
+
         __device__ __forceinline__ uint32_t flipped_index(const RenderParams &rp, uint32_t x, uint32_t y)
         {
             return (rp.w - 1 - x) + (rp.h - 1 - y) * rp.w;    // renderer.cpp:358-362
@@ -151,7 +161,7 @@ namespace crb
             const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
             if (slot >= rp.npix * rp.batch) return;
             const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
-            const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+            const uint32_t x = pix % rp.w, y = row_of(rp, pix / rp.w);
             const uint32_t sample = rp.first_sample + s;
             const uint32_t key    = path_key(rp.seed, x + y * rp.w, sample);
             const float    fx = (float(x) + rnd(key, 0)) / float(rp.w), fy = (float(y) + rnd(key, 1)) / float(rp.h);    // renderer.cpp:260-263
@@ -356,7 +366,7 @@ namespace crb
                     const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
                     V3           thr = v3(t4.x, t4.y, t4.z);
                     const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
-                    const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+                    const uint32_t x = pix % rp.w, y = row_of(rp, pix / rp.w);
                     const uint32_t sample = rp.first_sample + s;
                     const bool     aov    = (i == 0) && (sample == rp.aov_sample);
 
@@ -548,7 +558,7 @@ namespace crb
                     const V3     thr = v3(t4.x, t4.y, t4.z);
                     const bool   specular = t4.w != 0.0f;
                     const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
-                    const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+                    const uint32_t x = pix % rp.w, y = row_of(rp, pix / rp.w);
                     const uint32_t sample = rp.first_sample + s;
                     const bool     aov    = (i == 0) && (sample == rp.aov_sample);
                     const uint32_t key    = path_key(rp.seed, x + y * rp.w, sample);
@@ -835,19 +845,15 @@ namespace crb
             c[CTR_CUR_TRACE] = c[CTR_CUR_SHADE] = c[CTR_CUR_SHADOW] = 0;
         }
 
-        __device__ __forceinline__ float4 resolve_px(float4 a, float n)
-        {
-            // renderer.cpp:371-383
-            const float g = 1.f / 2.2f;
-            return make_float4(powf(clampf(a.x / n, 0.0f, 1.0f), g), powf(clampf(a.y / n, 0.0f, 1.0f), g), powf(clampf(a.z / n, 0.0f, 1.0f), g), 1.0f);
-        }
-
         // ------------------------------------------------------------------ K9 accumulate + resolve
-        __global__ void __launch_bounds__(256) k_accumulate(RenderParams rp, PathState ps, uint32_t passes_after)
+        // accum.w is the PER-PIXEL pass count: a render call may cover a row band only (crb_render_set_rows, the tile
+        // partition), so one counter per renderer would divide later bands by the wrong count and a RAW_SUM read
+        // would not be a complete checkpoint. The display is resolved with the pixel's own count.
+        __global__ void __launch_bounds__(256) k_accumulate(RenderParams rp, PathState ps)
         {
             const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
             if (pix >= rp.npix) return;
-            const uint32_t x = pix % rp.w, y = rp.row0 + pix / rp.w;
+            const uint32_t x = pix % rp.w, y = row_of(rp, pix / rp.w);
             const uint32_t fi = flipped_index(rp, x, y);
             float4         a  = rp.accum[fi];
             for (uint32_t s = 0; s < rp.batch; s++)
@@ -855,17 +861,23 @@ namespace crb
                 const float4 r = ps.rad[size_t(s) * rp.npix + pix];    // coalesced float4, sample order = the reference's pass order
                 a.x += r.x, a.y += r.y, a.z += r.z;
             }
-            a.w           = float(passes_after);
-            rp.accum[fi]  = a;
-            rp.display[fi] = resolve_px(a, float(passes_after));
+            a.w += float(rp.batch);
+            rp.accum[fi]   = a;
+            rp.display[fi] = resolve_px(a, a.w);
         }
 
-        __global__ void __launch_bounds__(256) k_resolve(const float4 *__restrict__ accum, float4 *__restrict__ display, uint32_t n, uint32_t passes)
+        __global__ void __launch_bounds__(256) k_resolve(const float4 *__restrict__ accum, float4 *__restrict__ display, uint32_t n)
         {
             const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= n) return;
-            float4 a   = accum[i];
-            display[i] = resolve_px(a, float(passes));
+            const float4 a = accum[i];
+            if (a.w > 0.0f) display[i] = resolve_px(a, a.w);    // pixels without a sample keep cr::image's FLT_MAX fill
+        }
+
+        __global__ void __launch_bounds__(256) k_set_pass_count(float4 *__restrict__ accum, uint32_t n, float passes)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i < n) accum[i].w = passes;
         }
 
         __global__ void k_fill4(float4 *p, uint32_t n, float4 v)
@@ -880,7 +892,7 @@ namespace crb
         : scene(s), w(w_), h(h_), max_bounces(mb), seed(seed_), flags(flags_), row0(0), row1(h_)
     {
 #ifndef CRB_EMU
-        CRB_CUDA_CHECK(cudaSetDevice(s->device));
+        // (the C ABI runs every call under the handle's device, capi.cu DeviceScope)
         n_sms = s->n_sms;    // (cudaGetDeviceProperties costs tens of milliseconds; the scene already asked)
         // experiment knob: keep the context's local-memory reservation at its high-water mark (the traversal stack lives in
         // local memory; by default the driver may shrink the reservation when the device idles and re-grow it at a launch)
@@ -929,14 +941,14 @@ namespace crb
         CRB_LAUNCH(k_fill4, g, 256, stream(), depth.p, n, fm);
         dev_zero(dstats.p, ST_COUNT * 8, stream());
         dev_zero(counters.p, CTR_COUNT * 4, stream());
-        passes = 0, device_ms = 0, launches = 0, pixel_samples = 0;
+        passes = 0, pass_px = 0, device_ms = 0, launches = 0, pixel_samples = 0;
         for (int i = 0; i < 8; i++) kernel_ms[i] = 0, kernel_count[i] = 0;
     }
 
     void Render::set_resolution(uint32_t w_, uint32_t h_)
     {
         sync();
-        w = w_, h = h_, row0 = 0, row1 = h_;
+        w = w_, h = h_, row0 = 0, row1 = h_, band = 0;
         alloc_images();
         scene_version = ~0ull;
         reset();
@@ -947,6 +959,17 @@ namespace crb
         if (y1 > h) y1 = h;
         if (y0 >= y1) throw Error(ERR_INVALID_ARG, "set_rows: empty row range");
         row0 = y0, row1 = y1;
+        band = 0;
+    }
+
+    void Render::set_bands(uint32_t band_rows, uint32_t first, uint32_t stride)
+    {
+        if (band_rows == 0 || stride == 0 || first >= stride) throw Error(ERR_INVALID_ARG, "set_bands: need band_rows > 0 and first < stride");
+        uint32_t rows = 0;
+        for (uint32_t y0 = first * band_rows; y0 < h; y0 += stride * band_rows) rows += std::min(band_rows, h - y0);
+        // rows == 0 is legal: more ranks than bands, this rank renders nothing
+        band = band_rows, band_first = first, band_stride = stride, band_nrows = rows;
+        row0 = 0, row1 = h;
     }
 
     void Render::refresh()
@@ -1041,8 +1064,9 @@ namespace crb
         if (n == 0) return;
         if (scene_version != scene->version) refresh();
         collect_time(false);
-        const uint32_t nrows = row1 - row0;
+        const uint32_t nrows = band ? band_nrows : row1 - row0;
         const uint32_t npix  = w * nrows;
+        if (npix == 0) return;
         // CRB_SUBMIT_DEBUG=1: host-clock breakdown of this call's submission on stderr (measurement hook)
         static const bool submit_debug = getenv("CRB_SUBMIT_DEBUG") && atoi(getenv("CRB_SUBMIT_DEBUG"));
         const auto        now          = [] { return std::chrono::steady_clock::now(); };
@@ -1084,6 +1108,7 @@ namespace crb
 
         RenderParams rp {};
         rp.w = w, rp.h = h, rp.row0 = row0, rp.nrows = nrows, rp.npix = npix, rp.seed = seed;
+        rp.band = band, rp.band_first = band_first, rp.band_stride = band_stride;
         rp.aov_sample = first + n - 1;
         rp.accum = accum.p, rp.display = display.p, rp.albedo = albedo.p, rp.normal = normal.p, rp.depth = depth.p;
 
@@ -1169,16 +1194,18 @@ namespace crb
                 launches++;
                 std::swap(ps.q_in, ps.q_next);
             }
-            passes += b;
 #ifdef CRB_EMU
-            CRB_LAUNCH(k_accumulate, npix, 1, st, rp, ps, passes);
+            CRB_LAUNCH(k_accumulate, npix, 1, st, rp, ps);
 #else
             tick(CRB_K_ACCUMULATE);
-            CRB_LAUNCH(k_accumulate, (npix + 255) / 256, 256, st, rp, ps, passes);
+            CRB_LAUNCH(k_accumulate, (npix + 255) / 256, 256, st, rp, ps);
             tock();
 #endif
             launches++;
             pixel_samples += uint64_t(np);
+            // _current_sample of the reference counts whole-frame passes; with row bands that is pixel-samples / frame
+            pass_px += uint64_t(np);
+            passes = uint32_t(pass_px / (uint64_t(w) * h));
         }
 #ifndef CRB_EMU
         CRB_CUDA_CHECK(cudaEventRecord(span.b, stream()));
@@ -1202,10 +1229,21 @@ namespace crb
     {
         const uint32_t n = w * h;
 #ifdef CRB_EMU
-        CRB_LAUNCH(k_resolve, n, 1, stream(), accum.p, display.p, n, passes ? passes : 1u);
+        CRB_LAUNCH(k_resolve, n, 1, stream(), accum.p, display.p, n);
 #else
-        CRB_LAUNCH(k_resolve, (n + 255) / 256, 256, stream(), accum.p, display.p, n, passes ? passes : 1u);
+        CRB_LAUNCH(k_resolve, (n + 255) / 256, 256, stream(), accum.p, display.p, n);
 #endif
+    }
+
+    void Render::set_pass_count(uint32_t passes_)
+    {
+        const uint32_t n = w * h;
+#ifdef CRB_EMU
+        CRB_LAUNCH(k_set_pass_count, n, 1, stream(), accum.p, n, float(passes_));
+#else
+        CRB_LAUNCH(k_set_pass_count, (n + 255) / 256, 256, stream(), accum.p, n, float(passes_));
+#endif
+        passes = passes_, pass_px = uint64_t(passes_) * w * h;
     }
 
     const float4 *Render::buffer_of(int kind) const
@@ -1276,7 +1314,7 @@ namespace crb
         sync();
         dev_upload(accum.p, raw_sum_rgba, size_t(w) * h * 16, stream());
         stream_sync(stream());
-        passes = passes_;
+        passes = passes_, pass_px = uint64_t(passes_) * w * h;    // the per-pixel counts travel in the image's alpha
         resolve();
         sync();
     }

@@ -32,6 +32,14 @@ namespace crb
     enum { CTR_IN = 0, CTR_CLASS0 = 1, CTR_NEXT = 5, CTR_SHADOW = 6, CTR_CUR_TRACE = 7, CTR_CUR_SHADE = 8, CTR_CUR_SHADOW = 9, CTR_COUNT = 16 };
     enum { ST_CLOSEST = 0, ST_SHADOW = 1, ST_RANOUT = 2, ST_NODES = 3, ST_TRIS = 4, ST_NODES_SHADOW = 5, ST_TRIS_SHADOW = 6, ST_COUNT = 8 };
 
+    // display = pow(clamp(sum / n, 0, 1), 1/2.2), alpha 1 (renderer.cpp:371-383); shared by the single-GPU accumulate
+    // and the multi-GPU merge kernels so that both resolve with the same operations
+    __device__ __forceinline__ float4 resolve_px(float4 a, float n)
+    {
+        const float g = 1.f / 2.2f;
+        return make_float4(powf(clampf(a.x / n, 0.0f, 1.0f), g), powf(clampf(a.y / n, 0.0f, 1.0f), g), powf(clampf(a.z / n, 0.0f, 1.0f), g), 1.0f);
+    }
+
     struct RenderParams
     {
         uint32_t w, h, row0, nrows, npix;    // npix = w * nrows (pixels rendered per pass)
@@ -39,6 +47,7 @@ namespace crb
         uint32_t first_sample, batch;        // this batch renders global samples first_sample .. +batch-1
         uint32_t aov_sample;                 // global sample index whose first hit is written to the AOVs
         uint32_t bounce;
+        uint32_t band, band_first, band_stride;    // band != 0: local rows are interleaved bands (tile partition), see row_of()
         float4  *accum, *display, *albedo, *normal, *depth;
     };
 
@@ -47,7 +56,9 @@ namespace crb
         Scene   *scene;
         uint32_t w, h, max_bounces, seed, flags;
         uint32_t row0, row1;
-        uint32_t passes = 0;
+        uint32_t band = 0, band_first = 0, band_stride = 1, band_nrows = 0;    // set_bands(): interleaved row bands instead of [row0,row1)
+        uint32_t passes = 0;     // whole-frame passes completed (_current_sample): pass_px / (w*h)
+        uint64_t pass_px = 0;    // pixel-samples accumulated (incl. a restored checkpoint's)
         uint64_t scene_version = ~0ull;
         DScene   dscene;
 
@@ -105,10 +116,12 @@ namespace crb
         void reset();
         void set_resolution(uint32_t w, uint32_t h);
         void set_rows(uint32_t y0, uint32_t y1);
+        void set_bands(uint32_t band_rows, uint32_t first, uint32_t stride);
         void refresh();
         void render_samples(uint32_t first, uint32_t n);
         void sync();
         void resolve();
+        void set_pass_count(uint32_t passes_);
         void read(int kind, float *dst);
         uint64_t read_async(int kind, float *dst);
         void     read_wait(uint64_t ticket);

@@ -132,7 +132,7 @@ namespace crb
         m.transforms.assign(I, I + 16);
         models.push_back(std::move(m));
         committed = false;
-        version++;
+        version++, geom_version++;
         return int(models.size()) - 1;
     }
 
@@ -150,7 +150,7 @@ namespace crb
         if (committed && same_count)
             upload_materials();    // material edits do not need a rebuild (ui.h:924-929 path)
         else
-            committed = false;
+            committed = false, geom_version++;
     }
 
     void Scene::set_instances(int model, const float *mats, uint32_t n)
@@ -158,7 +158,7 @@ namespace crb
         if (model < 0 || size_t(model) >= models.size() || (!mats && n)) throw Error(ERR_INVALID_ARG, "set_instances: bad arguments");
         models[size_t(model)].transforms.assign(mats, mats + size_t(n) * 16);
         committed = false;
-        version++;
+        version++, geom_version++;
     }
 
     int Scene::add_texture(const float *rgba, uint32_t w, uint32_t h)
@@ -169,7 +169,7 @@ namespace crb
         t.rgba.assign(rgba, rgba + size_t(w) * h * 4);
         textures.push_back(std::move(t));
         committed = false;
-        version++;
+        version++, geom_version++;
         return int(textures.size()) - 1;
     }
 
@@ -344,6 +344,39 @@ namespace crb
         build_bvh8(d_wverts.p, n_flat, stream, opt, d_nodes, d_tris, build);
         d_wverts.release();
         committed = true;
+        version++;
+    }
+
+    void Scene::copy_description_from(const Scene &src)
+    {
+        models = src.models, textures = src.textures;
+        skybox = src.skybox, sky_w = src.sky_w, sky_h = src.sky_h;
+        d_skybox.release();    // commit() uploads it again
+        src_sky_version = src.sky_version;
+        copy_light_state_from(src);
+        committed = false;
+        version++, geom_version++;
+    }
+
+    void Scene::copy_light_state_from(const Scene &src)
+    {
+        sun = src.sun, sun_enabled = src.sun_enabled, camera = src.camera;
+        sky_rot[0] = src.sky_rot[0], sky_rot[1] = src.sky_rot[1];
+        if (src_sky_version != src.sky_version)
+        {
+            skybox = src.skybox, sky_w = src.sky_w, sky_h = src.sky_h;
+            src_sky_version = src.sky_version;
+            if (committed) upload_skybox();
+        }
+        bool mats_differ = models.size() != src.models.size();
+        for (size_t i = 0; i < models.size() && !mats_differ; i++)
+            mats_differ = models[i].materials.size() != src.models[i].materials.size() ||
+                          memcmp(models[i].materials.data(), src.models[i].materials.data(), models[i].materials.size() * sizeof(crb_material)) != 0;
+        if (mats_differ && models.size() == src.models.size())
+        {
+            for (size_t i = 0; i < models.size(); i++) models[i].materials = src.models[i].materials;
+            if (committed) upload_materials();
+        }
         version++;
     }
 

@@ -210,6 +210,8 @@ namespace crb
         // device state (valid after commit)
         bool             committed = false;
         uint64_t         version   = 0;    // bumped by every mutation/commit; renderers refresh on change
+        uint64_t         geom_version = 0; // bumped by mutations that need a commit (meshes, instances, textures, material count)
+        uint64_t         sky_version  = 0; // bumped when the skybox image changes
         DBuf<float>      d_wverts;         // kept only during the build
         DBuf<float4>     d_shade_tri;
         DBuf<float>      d_obj_uvs;
@@ -241,6 +243,10 @@ namespace crb
         void upload_skybox();
         DScene device_scene(uint32_t w, uint32_t h) const;    // camera aspect from the render target
         void   require_committed() const;
+        // multi-GPU replicas (multi.cu): the host-side description of another scene, to be committed on this scene's GPU
+        void copy_description_from(const Scene &src);
+        void copy_light_state_from(const Scene &src);    // camera, sun, materials, skybox: no rebuild
+        uint64_t src_sky_version = ~0ull;
     };
 
     // batch queries (trace.cu)

@@ -1,4 +1,9 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed for the collective.
+"""Multi-GPU plumbing for a Python host with one process per GPU (torchrun).
+
+The multi-GPU path itself lives in the library (csrc/multi.cu): replicas, partition, NCCL merge on a side stream
+with the resolve fused behind it. This module only (a) carries the 128-byte NCCL id from rank 0 to the other ranks
+over torch.distributed and creates the rank handle (`rank_renderer`), and (b) keeps the pure host-side partition
+arithmetic + a bring-your-own-collective merge that the world_size-2 gloo tests on CPU exercise.
 
 The path shards with NO data-path exchange: every pixel-sample is independent
 (_sample_pixel only touches its own pixel, src/render/renderer.cpp:362-383) and the scene is read-only
@@ -83,3 +88,31 @@ def merge_renderer(rend, partition: str = "spp", passes_local=None) -> int:
     rend.resolve()
     rend.sync()
     return passes
+
+
+def comm_unique_id(lib_path=None) -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls this; the bytes go to every rank by any means)."""
+    import ctypes as C
+
+    from . import _capi
+
+    lib = _capi.load(lib_path)
+    buf = C.create_string_buffer(128)
+    _capi.check(lib, lib.crb_comm_unique_id(buf))
+    return buf.raw
+
+
+def rank_renderer(res_x, res_y, bounces, scn, partition="spp", seed=0, **kw):
+    """One process per GPU: every rank passes its own committed copy of the scene; rank 0's NCCL id is broadcast over
+    torch.distributed (any backend), then the library owns the communicator (crb_render_create_rank) and
+    renderer.render / current_progress / raw_sum work on the MERGED image like on one GPU."""
+    import torch.distributed as dist
+
+    from . import api
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    part = api.PARTITION_TILE if partition in ("tile", api.PARTITION_TILE) else api.PARTITION_SPP
+    return api.renderer(res_x, res_y, bounces, scn, seed=seed, partition=part, comm=(box[0], rank, world), **kw)

@@ -4,7 +4,7 @@
 // with the Python API.
 //
 //   g++ -std=c++17 -O2 crender_cli.cpp -o crender_cli -L.. -lcrender_b200 -Wl,-rpath,'$ORIGIN/..'
-//   ./crender_cli out.bin [w h spp bounces seed]
+//   ./crender_cli [--gpus N] [--partition spp|tile] out.bin [w h spp bounces seed]     N GPUs of this process (crb_render_create_multi)
 //   ./crender_cli --obj model.obj name PNG|HDR|EXR [w h spp bounces]     what the reference's "load model" + "export"
 //                 panels do (src/ui/ui.h:567-631, asset_loader.cpp:182-377): OBJ/MTL/PNG textures in, ./out/name.ext out,
 //                 camera on the -Z side framing the model's bounds, default sun
@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 
 namespace
 {
@@ -63,6 +64,8 @@ namespace
     }
 }    // namespace
 
+static int g_gpus = 1, g_partition = CRB_PARTITION_SPP;
+
 static int render_obj(int argc, char **argv)
 {
     namespace al = crb::asset_loader;
@@ -81,7 +84,9 @@ static int render_obj(int argc, char **argv)
     cam.position    = { 0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), lo[2] - 0.75f * ext / std::tan(20.0f * float(M_PI) / 180.0f) - 0.05f * ext };
     scn.set_camera(cam);
     const crb_build_info info = scn.commit();
-    crb::renderer        r(uint64_t(w), uint64_t(h), uint64_t(bounces), &scn, 0);
+    std::unique_ptr<crb::renderer> rp(g_gpus > 1 ? new crb::renderer(uint64_t(w), uint64_t(h), uint64_t(bounces), &scn, 0, g_gpus, g_partition)
+                                                 : new crb::renderer(uint64_t(w), uint64_t(h), uint64_t(bounces), &scn, 0));
+    crb::renderer &r = *rp;
     r.set_target_spp(uint64_t(spp));
     r.start();
     const crb_stats   st   = r.current_stats();
@@ -94,6 +99,16 @@ static int render_obj(int argc, char **argv)
 
 int main(int argc, char **argv)
 {
+    // leading options: --gpus N, --partition spp|tile
+    while (argc > 2 && (std::string(argv[1]) == "--gpus" || std::string(argv[1]) == "--partition"))
+    {
+        if (std::string(argv[1]) == "--gpus")
+            g_gpus = atoi(argv[2]);
+        else
+            g_partition = std::string(argv[2]) == "tile" ? CRB_PARTITION_TILE : CRB_PARTITION_SPP;
+        argv[2] = argv[0];
+        argv += 2, argc -= 2;
+    }
     if (argc > 2 && std::string(argv[1]) == "--obj")
     {
         try
@@ -118,11 +133,14 @@ int main(int argc, char **argv)
         cam.position = { 0.0f, 0.0f, -3.4f }, cam.fov = 40.0f;
         scn.set_camera(cam);
         const crb_build_info info = scn.commit();
-        crb::renderer        r(uint64_t(w), uint64_t(h), uint64_t(bounces), &scn, uint32_t(seed));
+        std::unique_ptr<crb::renderer> rp(g_gpus > 1 ? new crb::renderer(uint64_t(w), uint64_t(h), uint64_t(bounces), &scn, uint32_t(seed), g_gpus, g_partition)
+                                                     : new crb::renderer(uint64_t(w), uint64_t(h), uint64_t(bounces), &scn, uint32_t(seed)));
+        crb::renderer &r = *rp;
         r.set_target_spp(uint64_t(spp));
         r.start();
         const crb_stats  st = r.current_stats();
         const crb::image im = r.current_progress();
+        if (g_gpus > 1) std::printf("%d GPUs, %s partition: ", g_gpus, g_partition == CRB_PARTITION_TILE ? "tile" : "spp");
         std::printf("cornell %dx%d %d spp: %llu triangles, %llu nodes, build %.3f ms, %llu queries in %.3f ms device time (%.1f Mrays/s)\n", w, h, spp,
                     (unsigned long long) info.n_triangles, (unsigned long long) info.n_nodes, info.build_ms, (unsigned long long) st.total_queries,
                     st.device_ms, st.device_ms > 0 ? double(st.total_queries) / st.device_ms / 1e3 : 0.0);

@@ -36,6 +36,7 @@ typedef enum crb_status
     CRB_ERR_NO_DEVICE     = 10,
     CRB_ERR_CUDA          = 11,
     CRB_ERR_OOM           = 12,
+    CRB_ERR_NCCL          = 13, /* NCCL not loadable / a collective failed (multi-GPU handles only) */
     CRB_ERR_BUILD_VERTS   = 30, /* data/errors.json "30": could not create vertex buffer */
     CRB_ERR_BUILD_INDEX   = 31, /* data/errors.json "31": could not create index buffer */
     CRB_ERR_BVH_DEPTH     = 32,
@@ -86,7 +87,8 @@ typedef struct crb_ray
 /* RTCHit subset + which model/instance (cr::ray::intersection_record, src/render/ray.h:15-23) */
 typedef struct crb_hit
 {
-    float    t; /* +inf on miss, in units of |d| */
+    float    t; /* +inf on miss, in units of |d|: the batch query does NOT normalise d (rtcIntersect1's own convention);
+                   scene::cast_ray's callers get world-space distances because model.cpp:110 normalises first — pass unit d */
     float    u, v;
     uint32_t prim;  /* triangle index inside the model, 0xffffffff on miss */
     uint32_t model; /* model id, 0xffffffff on miss */
@@ -200,15 +202,20 @@ int crb_render_set_resolution(crb_render *, uint32_t w, uint32_t h); /* renderer
 int crb_render_set_max_bounces(crb_render *, uint32_t bounces);      /* renderer.cpp:210-213 */
 /* picks up scene-side changes made since create (camera, sun, materials, re-commit) */
 int crb_render_refresh(crb_render *);
-/* restrict rendering to pixel rows [y0,y1) in sample space (tile partition); default full frame */
+/* restrict rendering to pixel rows [y0,y1) in sample space; default full frame. The reference's unit of work is one
+ * scanline task (renderer.cpp:246-253); a row range is a set of them. */
 int crb_render_set_rows(crb_render *, uint32_t y0, uint32_t y1);
+/* ... or to interleaved row bands: bands of band_rows rows, this handle renders band `first`, first+stride, ... in ONE
+ * launch sequence (what a rank of the tile partition renders). Single-GPU handles only. */
+int crb_render_set_bands(crb_render *, uint32_t band_rows, uint32_t first, uint32_t stride);
 /* n progressive passes, global sample indices first_sample..first_sample+n-1
  * (management thread + _get_tasks + _sample_pixel, renderer.cpp:116-144,240-384); asynchronous */
 int crb_render_samples(crb_render *, uint32_t first_sample, uint32_t n);
 int crb_render_sync(crb_render *);
 enum { CRB_RAW_SUM = 0, CRB_PROGRESS = 1, CRB_ALBEDO = 2, CRB_NORMAL = 3, CRB_DEPTH = 4 };
 /* current_progress/normals/albedos/depths (renderer.cpp:220-238): w*h*4 floats, row-major, x/y
- * flipped exactly as the reference stores them. CRB_RAW_SUM = _raw_buffer as RGBA with A = passes. */
+ * flipped exactly as the reference stores them. CRB_RAW_SUM = _raw_buffer as RGBA with A = the pixel's own pass
+ * count (a render call may cover a row range only), so a RAW_SUM read is a complete checkpoint. */
 int crb_render_read(crb_render *, int kind, float *dst_host);
 /* The reference's UI thread reads those buffers while the workers keep rendering (lock-free getters,
  * renderer.cpp:220-238; display loop src/display/display.cpp:200-220). crb_render_read_async queues a consistent
@@ -227,9 +234,37 @@ int crb_render_restore(crb_render *, const float *raw_sum_rgba_host, uint32_t pa
  * form takes any host RGBA image, the second the renderer's device-resident display buffer. */
 int crb_post_process(crb_scene *, const float *rgba_host, uint32_t w, uint32_t h, const crb_post_settings *, float *out_host);
 int crb_render_post_process(crb_render *, const crb_post_settings *, float *out_host);
-/* multi-GPU plumbing: the float4 accumulation buffer (device pointer, w*h*4 floats) so that the
- * caller's collective (torch.distributed/NCCL) can reduce it in place, then set the merged pass count
- * and re-resolve the display buffer. */
+/* ---- multi-GPU. The reference is one process on one CPU; its management thread
+ * (src/render/renderer.cpp:116-144) issues passes and the UI reads the image (src/ui/ui.h:358-372). The same two calls
+ * — crb_render_samples and crb_render_read[_async] — drive N GPUs through a handle made by one of:
+ *   crb_render_create_multi  one process, N GPUs: the library replicates `scene` (host description copied, BVH built on
+ *                            every GPU), runs one submission thread per GPU and merges on side streams. With peer
+ *                            access the merge is one kernel per GPU over NVLink peer memory (sum in rank order +
+ *                            resolve, CRB_MERGE_PEER_KERNEL), else ncclCommInitAll + ncclAllReduce/ncclBroadcast.
+ *   crb_render_create_rank   one process per GPU (torchrun / MPI): rank 0 calls crb_comm_unique_id, the host
+ *                            broadcasts the 128 bytes by its own means, every rank creates its handle on its own
+ *                            committed copy of the scene; the merge is ncclAllReduce (spp) or an all-gather of the row
+ *                            bands as grouped ncclBroadcasts (tile) + the resolve behind it, on a side stream.
+ * partition: CRB_PARTITION_SPP — every crb_render_samples(first, n) range is split into contiguous shares, rank g
+ * renders samples [first + g*n/N, ...) of every pixel (BASELINE config 4); CRB_PARTITION_TILE — rank g renders all n
+ * samples of the 64-row bands g, g+N, ... (BASELINE config 5). The sampler is keyed by global pixel and sample index,
+ * so the union over ranks is the single-GPU set of paths; tile merges are bit-identical to one GPU, spp merges differ
+ * by float summation order only. crb_render_read / _read_async return the MERGED image (a flush is implied;
+ * crb_render_flush starts one early). In rank mode reading an AOV buffer is a collective call and crb_render_stats
+ * reports this rank's share. set_rows / set_bands / set_pass_count are single-GPU calls. NCCL is dlopen'ed
+ * ("libnccl.so.2", override with CRB_NCCL_LIB) at first use: CRB_ERR_NCCL if it is needed and missing. */
+enum { CRB_PARTITION_SPP = 0, CRB_PARTITION_TILE = 1 };
+enum { CRB_MERGE_NONE = 0, CRB_MERGE_PEER_KERNEL = 1, CRB_MERGE_NCCL = 2 };
+int crb_render_create_multi(crb_scene *, const int *devices_or_null, int ngpus, int partition, uint32_t w, uint32_t h, uint32_t max_bounces,
+                            uint32_t seed, uint32_t flags, crb_render **out);
+int crb_comm_unique_id(void *id128); /* ncclGetUniqueId */
+int crb_render_create_rank(crb_scene *, const void *id128, int rank, int nranks, int partition, uint32_t w, uint32_t h, uint32_t max_bounces,
+                           uint32_t seed, uint32_t flags, crb_render **out);
+int crb_render_flush(crb_render *); /* start merging the accumulators now (asynchronous); no-op on a single-GPU handle */
+int crb_render_info(crb_render *, int *ngpus_local, int *nranks, int *partition, int *merge_kind);
+/* plumbing for a host that brings its own collective: the float4 accumulation buffer (device pointer, w*h*4 floats;
+ * A = per-pixel pass count) to reduce in place, then crb_render_resolve re-resolves the display buffer with the
+ * per-pixel counts; crb_render_set_pass_count overwrites every pixel's count. */
 int crb_render_accum_ptr(crb_render *, void **device_ptr, uint64_t *n_floats);
 int crb_render_set_pass_count(crb_render *, uint32_t passes);
 int crb_render_resolve(crb_render *);

@@ -121,9 +121,27 @@ def check_partition_invariance(lib_path, desc, w, h, spp, bounces):
     r.render(spp, first_sample=0)
     r.set_rows(cut, h)
     r.render(spp, first_sample=0)
-    r.set_pass_count(spp)
-    r.resolve()
-    np.testing.assert_array_equal(r.raw_sum()[..., :3], whole[..., :3])
+    # the pass count is per pixel (accum.w), so the bands need no manual set_pass_count / resolve, and a RAW_SUM
+    # read after a banded render is a complete checkpoint (alpha == spp everywhere)
+    np.testing.assert_array_equal(r.raw_sum(), whole)
+    np.testing.assert_array_equal(r.current_progress(), disp)
+    assert r.current_stats().passes == spp
+    ck = r.checkpoint().copy()
+    r2 = api.renderer(w, h, bounces, g, seed=9)
+    r2.restore(ck)
+    assert r2.current_stats().passes == spp
+    r2.render(2)
+    r.set_rows(0, h)
+    r.render(2, first_sample=spp)
+    np.testing.assert_array_equal(r2.raw_sum(), r.raw_sum())
+    np.testing.assert_array_equal(r2.current_progress(), r.current_progress())
+    del r2
+    # interleaved bands in one launch sequence (what a tile-partition rank renders): 3 "ranks" cover the frame
+    r.start()
+    for first in range(3):
+        r.set_bands(7, first, 3)
+        r.render(spp, first_sample=0)
+    np.testing.assert_array_equal(r.raw_sum(), whole)
     np.testing.assert_array_equal(r.current_progress(), disp)
     # linearity of the accumulation: rendering spp twice from the same first sample doubles the sum
     r.set_rows(0, h)
@@ -547,3 +565,94 @@ def check_recycled_memory_is_clean(lib_path):
         np.testing.assert_array_equal(h0[k], h2[k])
     assert (h0["prim"] != h1["prim"]).any()  # the second scene really was different
 
+
+
+def check_multi_gpu_handle(lib_path, gpus, w=72, h=150, spp=6, bounces=5):
+    """crb_render_create_multi: one process, the devices in `gpus` (the kernel-logic harness ignores the ids: the
+    replicas, the partition and the merge run serially on the host). The tile partition must merge bit-identically
+    to a single renderer (row bands are disjoint and per-pixel sample order is unchanged), the spp partition up to
+    float summation order across ranks; AOVs, statistics, checkpoint/resume, resolution and scene edits follow."""
+    desc = scenes.textured_scene()
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    single = api.renderer(w, h, bounces, g, seed=11)
+    single.render(spp)
+    want_raw, want_disp = single.raw_sum().copy(), single.current_progress().copy()
+    want_aov = [single.current_albedos().copy(), single.current_normals().copy(), single.current_depths().copy()]
+    want_q = single.current_stats().total_queries
+    n = len(gpus)
+    for part in (api.PARTITION_TILE, api.PARTITION_SPP):
+        m = api.renderer(w, h, bounces, g, seed=11, gpus=gpus, partition=part)
+        info = m.info()
+        assert info["gpus_local"] == n and info["ranks"] == n and info["partition"] == ("spp", "tile")[part]
+        assert info["merge"] in (("none",) if n == 1 else ("peer-kernel", "nccl"))
+        # progressive: two calls, a read in between (flush + merge), one more call
+        m.render(spp // 2, sync=False)
+        half = m.raw_sum().copy()
+        assert np.all(half[..., 3] == spp // 2)
+        m.render(spp - spp // 2, sync=False)
+        raw, disp = m.raw_sum().copy(), m.current_progress().copy()
+        np.testing.assert_array_equal(raw[..., 3], want_raw[..., 3])
+        if part == api.PARTITION_TILE or n == 1:
+            np.testing.assert_array_equal(raw, want_raw)
+            np.testing.assert_array_equal(disp, want_disp)
+        else:
+            assert common.relrmse(raw[..., :3], want_raw[..., :3]) < 1e-6
+            np.testing.assert_allclose(disp, want_disp, rtol=0, atol=1e-5)
+        for got, want in zip((m.current_albedos(), m.current_normals(), m.current_depths()), want_aov):
+            np.testing.assert_array_equal(got, want)
+        st = m.current_stats()
+        assert st.passes == spp and st.pixel_samples == w * h * spp and st.total_queries == want_q
+        # asynchronous merged read, then checkpoint -> restore into a fresh multi handle -> continue == single
+        out = np.zeros((h, w, 4), np.float32)
+        m.wait_read(m.current_progress_async(out))
+        np.testing.assert_array_equal(out, disp)
+        ck = m.checkpoint().copy()
+        m2 = api.renderer(w, h, bounces, g, seed=11, gpus=gpus, partition=part)
+        m2.restore(ck)
+        assert m2.current_stats().passes == spp
+        m2.render(2, first_sample=spp)
+        single.render(2, first_sample=spp)
+        if part == api.PARTITION_TILE or n == 1:
+            np.testing.assert_array_equal(m2.raw_sum(), single.raw_sum())
+        else:
+            assert common.relrmse(m2.raw_sum()[..., :3], single.raw_sum()[..., :3]) < 1e-6
+        del m2
+        single.start()
+        single.render(spp)
+        # scene edits reach the replicas through update(): camera (light state) and instances (re-commit everywhere)
+        cam2 = api.camera(position=(0.2, 1.1, -3.0), fov=60.0, rotation=(-2.0, 9.0, 0.0))
+        inst = np.stack([scenes.translation(-0.8, 0.0, 1.0), scenes.compose(scenes.translation(0.9, 0.1, 1.6), scenes.rotation_y(-20.0))]).astype(np.float32)
+
+        def mutate():
+            g.set_camera(cam2)
+            g.set_instances(2, inst)
+            g.commit()
+
+        m.update(mutate)
+        m.render(3)
+        s2 = api.renderer(w, h, bounces, g, seed=11)
+        s2.render(3)
+        if part == api.PARTITION_TILE or n == 1:
+            np.testing.assert_array_equal(m.raw_sum(), s2.raw_sum())
+        else:
+            assert common.relrmse(m.raw_sum()[..., :3], s2.raw_sum()[..., :3]) < 1e-6
+        m.set_resolution(40, 70)
+        m.render(2)
+        s2.set_resolution(40, 70)
+        s2.render(2)
+        if part == api.PARTITION_TILE or n == 1:
+            np.testing.assert_array_equal(m.current_progress(), s2.current_progress())
+        else:
+            np.testing.assert_allclose(m.current_progress(), s2.current_progress(), rtol=0, atol=1e-5)
+        # single-GPU-only calls are refused on a multi handle, with a message
+        with pytest.raises(api.CrbError):
+            m.set_rows(0, 10)
+        del m, s2
+        # restore the scene for the next partition
+        g.set_camera(desc.cam)
+        g.set_instances(2, desc.meshes[2].instances)
+        g.commit()
+        single = api.renderer(w, h, bounces, g, seed=11)
+        single.render(spp)

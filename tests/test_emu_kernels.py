@@ -65,3 +65,9 @@ def test_instrumented_render_is_identical(emu_lib):
 
 def test_recycled_memory_is_clean(emu_lib):
     pc.check_recycled_memory_is_clean(emu_lib)
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_multi_gpu_handle(emu_lib, n):
+    # the multi-GPU orchestration (replicas, spp / tile partition, merge, AOV gather, restore) executed serially
+    pc.check_multi_gpu_handle(emu_lib, list(range(n)))
