@@ -335,6 +335,10 @@ class renderer:
         """Multi-GPU handles: start merging the accumulators now (asynchronous; the read calls imply it)."""
         _capi.check(self._lib, self._lib.crb_render_flush(self._h))
 
+    def join_flush(self):
+        """The render stream waits for the last merge (for device-side timing of a whole step)."""
+        _capi.check(self._lib, self._lib.crb_render_join_flush(self._h))
+
     def info(self) -> dict:
         a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
         _capi.check(self._lib, self._lib.crb_render_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))

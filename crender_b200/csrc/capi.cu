@@ -391,6 +391,12 @@ int crb_render_flush(crb_render *r)
         if (h.m) h.m->flush();
     });
 }
+int crb_render_join_flush(crb_render *r)
+{
+    return on_render(r, [&](crb_render &h) {
+        if (h.m) h.m->join_flush();
+    });
+}
 int crb_render_sync(crb_render *r)
 {
     return on_render(r, [&](crb_render &h) { h.m ? h.m->sync() : h.r->sync(); });

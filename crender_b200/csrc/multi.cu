@@ -638,6 +638,24 @@ namespace crb
         dirty = false;
     }
 
+    // makes every render stream wait for the last merge: an event the caller records on the handle's stream afterwards
+    // (crb_render_stream) then covers the collective and the resolve, so a whole step can be timed on the device
+    void MultiRender::join_flush()
+    {
+        if (flushes == 0) return;
+#ifndef CRB_EMU
+        const int k = int((flushes - 1) & 1);
+        for (auto &lp : locals)
+        {
+            DeviceScope ds(lp->device);
+            if (fused_peers)
+                for (auto &o : locals) CRB_CUDA_CHECK(cudaStreamWaitEvent(lp->render->stream(), o->merge_done[k], 0));
+            else
+                CRB_CUDA_CHECK(cudaStreamWaitEvent(lp->render->stream(), lp->merge_done[k], 0));
+        }
+#endif
+    }
+
     void MultiRender::sync()
     {
         for (auto &lp : locals) lp->worker->wait();

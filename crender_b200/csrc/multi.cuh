@@ -117,6 +117,7 @@ namespace crb
         void   refresh();
         void   render_samples(uint32_t first, uint32_t n);
         void   flush();    // asynchronous merge; implied by the read calls
+        void   join_flush();
         void   sync();
         void   read(int kind, float *dst);
         uint64_t read_async(int kind, float *dst);

@@ -105,7 +105,101 @@ namespace crb
 #endif
         };
 
-        constexpr uint64_t CHUNK = 1ull << 24;    // rays per staging chunk for host-pointer calls
+        constexpr uint64_t CHUNK = 1ull << 24;    // rays per kernel launch for device-pointer calls
+        constexpr uint64_t PIPE_CHUNK = 1ull << 22;    // rays per pipeline stage for host-pointer calls (128 MB in, 96 MB out)
+
+        void launch_batch(Scene &s, const DScene &sc, int mode, const float4 *rp, char *op, uint32_t cnt32, uint32_t *cursor, unsigned long long *ctr,
+                          cudaStream_t st)
+        {
+#ifdef CRB_EMU
+            const unsigned g = 1, blk = 1;
+#else
+            const unsigned g = unsigned(s.n_sms) * 4, blk = 256;
+#endif
+            dev_zero(cursor, 4, st);
+            switch (mode)
+            {
+            case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, st, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), cursor, ctr); break;
+            case 1: CRB_LAUNCH((k_occluded_batch<false>), g, blk, st, sc, rp, cnt32, reinterpret_cast<uint8_t *>(op), cursor, ctr); break;
+            case 2: CRB_LAUNCH((k_intersect_batch<true>), g, blk, st, sc, rp, cnt32, (crb_hit *) nullptr, cursor, ctr); break;
+            default: CRB_LAUNCH((k_occluded_batch<true>), g, blk, st, sc, rp, cnt32, (uint8_t *) nullptr, cursor, ctr); break;
+            }
+        }
+
+#ifndef CRB_EMU
+        // Host-pointer queries: upload, traversal and download of consecutive chunks overlap on three streams with two
+        // device slots (the reference calls cast_ray one ray at a time on the CPU; a host caller of the batch form has
+        // its rays in host memory). With pinned host memory the copies are truly asynchronous and the call runs at
+        // PCIe speed (32 B in + 24 B out per ray against ~0.05 ns of traversal); pageable memory still works, the
+        // driver then stages the copies.
+        struct BatchPipe
+        {
+            cudaStream_t up = nullptr, down = nullptr;
+            cudaEvent_t  up_done[2] = {}, comp_done[2] = {}, down_done[2] = {}, t0 = nullptr, t1 = nullptr;
+            BatchPipe()
+            {
+                CRB_CUDA_CHECK(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+                CRB_CUDA_CHECK(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; i++)
+                {
+                    CRB_CUDA_CHECK(cudaEventCreateWithFlags(&up_done[i], cudaEventDisableTiming));
+                    CRB_CUDA_CHECK(cudaEventCreateWithFlags(&comp_done[i], cudaEventDisableTiming));
+                    CRB_CUDA_CHECK(cudaEventCreateWithFlags(&down_done[i], cudaEventDisableTiming));
+                }
+                CRB_CUDA_CHECK(cudaEventCreate(&t0));
+                CRB_CUDA_CHECK(cudaEventCreate(&t1));
+            }
+            ~BatchPipe()
+            {
+                for (int i = 0; i < 2; i++)
+                {
+                    if (up_done[i]) cudaEventDestroy(up_done[i]);
+                    if (comp_done[i]) cudaEventDestroy(comp_done[i]);
+                    if (down_done[i]) cudaEventDestroy(down_done[i]);
+                }
+                if (t0) cudaEventDestroy(t0);
+                if (t1) cudaEventDestroy(t1);
+                if (up) cudaStreamDestroy(up);
+                if (down) cudaStreamDestroy(down);
+            }
+        };
+
+        void run_batch_pipelined(Scene &s, const DScene &sc, const crb_ray *rays, void *out, uint64_t n, int mode)
+        {
+            const size_t out_elem = mode == 0 ? sizeof(crb_hit) : 1;
+            BatchPipe    pp;
+            DBuf<float4> d_rays[2];
+            DBuf<char>   d_out[2];
+            DBuf<uint32_t> d_cursor;
+            DBuf<unsigned long long> d_ctr;
+            d_cursor.alloc(2), d_ctr.alloc(2);
+            const uint64_t cap = std::min<uint64_t>(PIPE_CHUNK, n);
+            for (int i = 0; i < 2; i++) d_rays[i].alloc(cap * 2), d_out[i].alloc(cap * out_elem);
+            CRB_CUDA_CHECK(cudaEventRecord(pp.t0, s.stream));
+            uint64_t ci = 0;
+            for (uint64_t off = 0; off < n; off += PIPE_CHUNK, ci++)
+            {
+                const int      k   = int(ci & 1);
+                const uint64_t cnt = std::min<uint64_t>(PIPE_CHUNK, n - off);
+                if (ci >= 2) CRB_CUDA_CHECK(cudaStreamWaitEvent(pp.up, pp.comp_done[k], 0));      // the slot's rays have been traced
+                CRB_CUDA_CHECK(cudaMemcpyAsync(d_rays[k].p, rays + off, cnt * sizeof(crb_ray), cudaMemcpyHostToDevice, pp.up));
+                CRB_CUDA_CHECK(cudaEventRecord(pp.up_done[k], pp.up));
+                CRB_CUDA_CHECK(cudaStreamWaitEvent(s.stream, pp.up_done[k], 0));
+                if (ci >= 2) CRB_CUDA_CHECK(cudaStreamWaitEvent(s.stream, pp.down_done[k], 0));   // the slot's results have left
+                launch_batch(s, sc, mode, d_rays[k].p, d_out[k].p, uint32_t(cnt), d_cursor.p + k, d_ctr.p, s.stream);
+                CRB_CUDA_CHECK(cudaEventRecord(pp.comp_done[k], s.stream));
+                CRB_CUDA_CHECK(cudaStreamWaitEvent(pp.down, pp.comp_done[k], 0));
+                CRB_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(out) + off * out_elem, d_out[k].p, cnt * out_elem, cudaMemcpyDeviceToHost, pp.down));
+                CRB_CUDA_CHECK(cudaEventRecord(pp.down_done[k], pp.down));
+            }
+            CRB_CUDA_CHECK(cudaStreamSynchronize(pp.down));
+            CRB_CUDA_CHECK(cudaEventRecord(pp.t1, s.stream));
+            CRB_CUDA_CHECK(cudaEventSynchronize(pp.t1));
+            float ms = 0;
+            CRB_CUDA_CHECK(cudaEventElapsedTime(&ms, pp.t0, pp.t1));
+            s.last_query_ms = ms;    // whole pipeline: copies included
+        }
+#endif
 
         // mode 0 closest, 1 any-hit, 2 counters(closest), 3 counters(any)
         void run_batch(Scene &s, const crb_ray *rays, void *out, uint64_t n, bool on_device, int mode, uint64_t *ctr_out)
@@ -113,6 +207,13 @@ namespace crb
             s.require_committed();
             if (n && (!rays || (mode < 2 && !out))) throw Error(ERR_INVALID_ARG, "batch query: null ray/result pointer");
             const DScene sc = s.device_scene(1, 1);
+#ifndef CRB_EMU
+            if (!on_device && mode < 2 && n > 0)
+            {
+                run_batch_pipelined(s, sc, rays, out, n, mode);
+                return;
+            }
+#endif
             Timer        timer(s.stream);
             double       ms = 0;
             DBuf<unsigned long long> d_ctr;
@@ -140,21 +241,8 @@ namespace crb
                     dev_upload(d_rays.p, rays + off, cnt * sizeof(crb_ray), s.stream);
                     rp = d_rays.p, op = d_out.p;
                 }
-#ifdef CRB_EMU
-                const unsigned g = 1, blk = 1;
-#else
-                const unsigned g = unsigned(s.n_sms) * 4, blk = 256;
-#endif
-                const uint32_t cnt32 = uint32_t(cnt);
-                dev_zero(d_cursor.p, 4, s.stream);
                 timer.start();
-                switch (mode)
-                {
-                case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), d_cursor.p, d_ctr.p); break;
-                case 1: CRB_LAUNCH((k_occluded_batch<false>), g, blk, s.stream, sc, rp, cnt32, reinterpret_cast<uint8_t *>(op), d_cursor.p, d_ctr.p); break;
-                case 2: CRB_LAUNCH((k_intersect_batch<true>), g, blk, s.stream, sc, rp, cnt32, (crb_hit *) nullptr, d_cursor.p, d_ctr.p); break;
-                default: CRB_LAUNCH((k_occluded_batch<true>), g, blk, s.stream, sc, rp, cnt32, (uint8_t *) nullptr, d_cursor.p, d_ctr.p); break;
-                }
+                launch_batch(s, sc, mode, rp, op, uint32_t(cnt), d_cursor.p, d_ctr.p, s.stream);
                 ms += timer.stop();
                 if (!on_device && mode < 2) dev_download(static_cast<char *>(out) + off * out_elem, d_out.p, cnt * out_elem, s.stream);
             }

@@ -261,6 +261,9 @@ int crb_comm_unique_id(void *id128); /* ncclGetUniqueId */
 int crb_render_create_rank(crb_scene *, const void *id128, int rank, int nranks, int partition, uint32_t w, uint32_t h, uint32_t max_bounces,
                            uint32_t seed, uint32_t flags, crb_render **out);
 int crb_render_flush(crb_render *); /* start merging the accumulators now (asynchronous); no-op on a single-GPU handle */
+/* the handle's render stream(s) wait for the last flush: an event recorded on crb_render_stream afterwards covers the
+ * collective + resolve (device timing of a whole step); no-op on a single-GPU handle */
+int crb_render_join_flush(crb_render *);
 int crb_render_info(crb_render *, int *ngpus_local, int *nranks, int *partition, int *merge_kind);
 /* plumbing for a host that brings its own collective: the float4 accumulation buffer (device pointer, w*h*4 floats;
  * A = per-pixel pass count) to reduce in place, then crb_render_resolve re-resolves the display buffer with the
