@@ -331,6 +331,18 @@ class renderer:
         """Interleaved row bands first, first+stride, ... of band_rows rows each, rendered as one launch sequence."""
         _capi.check(self._lib, self._lib.crb_render_set_bands(self._h, band_rows, first, stride))
 
+    def set_sample_table(self, table: Optional[np.ndarray]):
+        """A caller-supplied sample table float32 [n_samples, h*w, dims] replaces the hash sampler (ref-exact mode):
+        dimensions 0,1 jitter; 2+4i+{0,1} scatter of bounce i; 2+4i+{2,3} sun sample of bounce i. None removes it."""
+        if table is None:
+            _capi.check(self._lib, self._lib.crb_render_set_sample_table(self._h, None, 0, 0))
+            return
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        w, h = self._res
+        if t.ndim != 3 or t.shape[1] != w * h:
+            raise ValueError("table must be [n_samples, h*w, dims]")
+        _capi.check(self._lib, self._lib.crb_render_set_sample_table(self._h, _ptr(t), t.shape[0], t.shape[2]))
+
     def flush(self):
         """Multi-GPU handles: start merging the accumulators now (asynchronous; the read calls imply it)."""
         _capi.check(self._lib, self._lib.crb_render_flush(self._h))

@@ -53,7 +53,8 @@ def _load_texture(path: str) -> Optional[np.ndarray]:
 
 
 def load_model(file: str, folder: Optional[str] = None) -> model_data:
-    """cr::asset_loader::load_model. Polygons are fan-triangulated (what tinyobj does for convex faces).
+    """cr::asset_loader::load_model. Quads are split along the shorter diagonal, larger polygons fan-triangulated
+    (what the reference's vendored tinyobj does for quads / convex faces; checked against the compiled reference).
     Faces without a material get an extra default material appended (tinyobj reports id -1, which the
     reference would use to index materials[] out of bounds)."""
     folder = folder if folder is not None else os.path.dirname(os.path.abspath(file))
@@ -82,8 +83,16 @@ def load_model(file: str, folder: Optional[str] = None) -> model_data:
                 v = int(parts[0])
                 t = int(parts[1]) if len(parts) > 1 and parts[1] else 0
                 corners.append((v - 1 if v > 0 else len(verts) + v, (t - 1 if t > 0 else len(uvs) + t) if t else -1))
-            for k in range(1, len(corners) - 1):
-                for c in (corners[0], corners[k], corners[k + 1]):
+            tris = [(0, k, k + 1) for k in range(1, len(corners) - 1)]  # fan = tinyobj's ear clipping for convex faces
+            if len(corners) == 4 and all(0 <= c[0] < len(verts) for c in corners):
+                # tinyobj splits a quad along its SHORTER diagonal, in float (external/tinyobj/tinobj.h:1394-1490)
+                p = [np.asarray(verts[c[0]], np.float32) for c in corners]
+                a, b = p[2] - p[0], p[3] - p[1]
+                sqr02 = np.float32(a[0] * a[0] + a[1] * a[1]) + np.float32(a[2] * a[2])
+                sqr13 = np.float32(b[0] * b[0] + b[1] * b[1]) + np.float32(b[2] * b[2])
+                tris = [(0, 1, 2), (0, 2, 3)] if sqr02 < sqr13 else [(0, 1, 3), (1, 2, 3)]
+            for tri in tris:
+                for c in (corners[tri[0]], corners[tri[1]], corners[tri[2]]):
                     vi.append(c[0])
                     ti.append(c[1])
                 mi.append(cur_mat)
@@ -280,7 +289,7 @@ def export_framebuffer(buffer: np.ndarray, path: str, image_type: str = PNG, out
         if image_type == PNG:
             img.save(target, format="PNG")
         else:
-            img.convert("RGB").save(target, format="JPEG", quality=100)
+            img.convert("RGB").save(target, format="JPEG", quality=100, subsampling=0)  # stbi_write_jpg at quality 100: no chroma subsampling
     elif image_type == HDR:
         _write_hdr(target, np.asarray(buffer, np.float32))
     else:

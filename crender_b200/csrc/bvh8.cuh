@@ -32,6 +32,12 @@
 #define CRB_EARLY_POP 2    // 1: +0.7 %, 2 (predicated in-place loads): +4.3 % (profiles/r1g_sweeps.md section 6)
 #endif
 
+// Leaf phase of the persistent trace loop: 0 = every lane tests one of ITS OWN waiting triangles per iteration (r1); 1 = all
+// waiting triangles of the warp are redistributed over all 32 lanes and tested at once (see trace_persistent)
+#ifndef CRB_COOP_LEAF
+#define CRB_COOP_LEAF 0    // measured: 2891 vs 3277 Mrays/s on config 2 (profiles/r2_sweeps.md): the redistribution costs more than the idle lanes
+#endif
+
 namespace crb
 {
     constexpr int      BVH8_STACK      = 48;     // entries; the builder rejects deeper trees loudly
@@ -282,6 +288,19 @@ namespace crb
     // traversal state in registers. Lanes reconverge every STEPS node iterations, where finished rays are
     // handed to `sink` (which may itself use warp-aggregated queue pushes) and idle lanes are refilled.
     //
+    // Leaf phase (CRB_COOP_LEAF): a node visit leaves a lane with 0..24 triangles to test. Testing them one per lane per
+    // iteration (r1) kept ~11 of 32 lanes out of the node phase while they worked through their triangles, and ran the
+    // triangle test at ~8 active lanes (ncu r1j: 20-23 lanes per instruction overall). Now every iteration's waiting
+    // triangles of ALL lanes are written to a per-warp work list in shared memory (round k of the list = the k-th
+    // triangle of every lane that has one: positions from a ballot), and lane j tests work item j against the owner's
+    // ray (o, d, tmin in shared memory since the refill; the owner's current tfar by shuffle). Winners are merged per
+    // owner with a 64-bit shared-memory atomicMin on (t bits, prim) — t > 0, so the float order is the integer order and
+    // ties in t go to the lowest primitive id exactly as in the sequential loop (the accepted set {t <= tfar at the
+    // start} contains the sequential winner, and the lexicographic minimum of it IS the sequential winner). After the
+    // leaf phase no lane has triangles waiting, so every active lane takes part in every node phase. Visit order, hit
+    // records and traversal counters are bit-identical to the one-per-lane form (tests: check_instrumented_render_is_
+    // identical, the emu-vs-oracle exact comparisons, any-hit == closest-hit existence).
+    //
     //   source(idx, item, o, d, tmin, tmax)  loads work item idx (called by the lane that owns it)
     //   sink(valid, item, hit)               called by ALL lanes at a convergent point; valid lanes retire
     // `any` (any-hit vs closest-hit) is a RUN-TIME argument on purpose: both query kinds execute the same
@@ -292,6 +311,15 @@ namespace crb
     {
         const unsigned FULL = 0xffffffffu;
         const unsigned lane = crb_lane_id();
+#if CRB_COOP_LEAF
+        constexpr int TP_WARPS = 8;    // warps per CTA of every kernel that runs this loop (256 threads)
+        __shared__ float4             s_ray_o[TP_WARPS][CRB_WARP], s_ray_d[TP_WARPS][CRB_WARP];    // o.xyz,tmin | d.xyz
+        __shared__ uint2              s_item[TP_WARPS][CRB_WARP];                                  // triangle index, owner lane
+        __shared__ unsigned long long s_key[TP_WARPS][CRB_WARP];                                   // per owner: min (t bits << 32 | prim)
+        __shared__ float2             s_uv[TP_WARPS][CRB_WARP];                                    // per owner: the winner's barycentrics
+        const unsigned wib = (threadIdx.x / CRB_WARP) % TP_WARPS;
+        s_key[wib][lane]   = ~0ull;
+#endif
         uint2          stack[BVH8_STACK];
         int            sp = 0;
         bool           active = false, finished = false, exhausted = false;
@@ -341,6 +369,10 @@ namespace crb
                     {
                         float tmax;
                         source(idx, item, o, d, tmin, tmax);
+#if CRB_COOP_LEAF
+                        s_ray_o[wib][lane] = make_float4(o.x, o.y, o.z, tmin);
+                        s_ray_d[wib][lane] = make_float4(d.x, d.y, d.z, 0.0f);
+#endif
                         best = Hit { tmax, 0.0f, 0.0f, INVALID_PRIM };
                         if (bvh.n_nodes == 0)
                         {
@@ -403,6 +435,82 @@ namespace crb
                 if (active && (group.y & 0xff000000u) == 0u && sp > 0) group = stack[--sp];
 #endif
 #endif
+#if CRB_COOP_LEAF
+                // ---- leaf phase, warp-cooperative: all waiting triangles of all lanes, redistributed over the lanes
+                if (__ballot_sync(FULL, active && tgroup.y != 0u) != 0u)
+                {
+                    const unsigned lt    = (1u << lane) - 1u;
+                    unsigned       total = 0;
+                    for (;;)
+                    {
+                        // round: one more triangle from every lane that still has one
+                        const bool     have = active && tgroup.y != 0u;
+                        const unsigned m    = __ballot_sync(FULL, have);
+                        const unsigned n    = unsigned(__popc(m));
+                        if (n == 0u || total + n > unsigned(CRB_WARP))
+                        {
+                            // ---- flush: lane j tests work item j
+                            __syncwarp();
+                            const bool     mine  = lane < total;
+                            const uint2    wi    = mine ? s_item[wib][lane] : make_uint2(0u, lane);
+                            const unsigned owner = wi.y;
+                            const float    tf    = __shfl_sync(FULL, best.t, int(owner));
+                            bool               hit = false;
+                            unsigned long long key = ~0ull;
+                            float              t = 0.f, u = 0.f, v = 0.f;
+                            if (mine)
+                            {
+                                const float4 *tp = bvh.tris + size_t(wi.x) * 3;
+                                const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
+                                const float4  ro = s_ray_o[wib][owner], rd = s_ray_d[wib][owner];
+                                if (COUNT) ctr->tris++;
+                                hit = tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), ro.w, tf, t, u, v);
+                                if (hit)
+                                {
+                                    key = ((unsigned long long) __float_as_uint(t) << 32) | (unsigned long long) __float_as_uint(a.w);
+                                    atomicMin(&s_key[wib][owner], key);
+                                }
+                            }
+                            __syncwarp();
+                            if (hit && s_key[wib][owner] == key) s_uv[wib][owner] = make_float2(u, v);
+                            __syncwarp();
+                            {
+                                // owners take their winner (same rule as the sequential loop: t < best.t, or equal t and lower id)
+                                const unsigned long long k = s_key[wib][lane];
+                                if (k != ~0ull)
+                                {
+                                    const float    kt = __uint_as_float(unsigned(k >> 32));
+                                    const unsigned kp = unsigned(k & 0xffffffffull);
+                                    if (kt < best.t || kp < best.prim)
+                                    {
+                                        const float2 uv = s_uv[wib][lane];
+                                        best            = Hit { kt, uv.x, uv.y, kp };
+                                    }
+                                    if (any)
+                                    {
+                                        // any hit ends the query: drop all remaining work, the advance step below retires the ray
+                                        group.y  = 0u;
+                                        tgroup.y = 0u;
+                                        sp       = 0;
+                                    }
+                                    s_key[wib][lane] = ~0ull;
+                                }
+                            }
+                            __syncwarp();
+                            total = 0;
+                            if (n == 0u) break;
+                            continue;    // re-ballot: an any-hit may have emptied lanes
+                        }
+                        if (have)
+                        {
+                            const int i = __ffs(int(tgroup.y)) - 1;
+                            tgroup.y &= tgroup.y - 1;
+                            s_item[wib][total + unsigned(__popc(m & lt))] = make_uint2(tgroup.x + unsigned(i), lane);
+                        }
+                        total += n;
+                    }
+                }
+#else
                 // ---- leaf phase in lock step: ONE triangle per lane that has triangles waiting (an inner
                 // per-lane triangle loop was 52 % of k_trace's instructions at 2.7 active lanes; waiting for
                 // more lanes to have triangles was measured and is slower, profiles/r1c_sweeps.md §6)
@@ -432,6 +540,7 @@ namespace crb
                         }
                     }
                 }
+#endif
                 // ---- advance: nothing left in this node group -> pop, or retire the ray
                 if (active && tgroup.y == 0u && (group.y & 0xff000000u) == 0u)
                 {

@@ -450,6 +450,13 @@ int crb_render_set_pass_count(crb_render *r, uint32_t passes)
         h.r->set_pass_count(passes);
     });
 }
+int crb_render_set_sample_table(crb_render *r, const float *table, uint32_t n_samples, uint32_t dims)
+{
+    return on_render(r, [&](crb_render &h) {
+        single_only(h, "crb_render_set_sample_table");
+        h.r->set_sample_table(table, n_samples, dims);
+    });
+}
 int crb_render_resolve(crb_render *r)
 {
     return on_render(r, [&](crb_render &h) { h.m ? h.m->resolve() : h.r->resolve(); });

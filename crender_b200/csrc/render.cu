@@ -54,6 +54,14 @@ namespace crb
         }
         __device__ __forceinline__ float rnd(uint32_t key, uint32_t dim) { return float(mix32(key + dim * 0x9e3779b9u) >> 8) * (1.0f / 16777216.0f); }
 
+        // a caller-supplied sample table (crb_render_set_sample_table) replaces the hash: [sample][pixel][dimension]
+        __device__ __forceinline__ float rnd_dim(const RenderParams &rp, uint32_t key, uint32_t pixel, uint32_t sample, uint32_t dim)
+        {
+            if (rp.table && sample < rp.table_samples && dim < rp.table_dims)
+                return rp.table[(size_t(sample) * rp.w * rp.h + pixel) * rp.table_dims + dim];
+            return rnd(key, dim);
+        }
+
         __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
 
         // k_shade's path record: all slot-indexed 16-byte loads issued together right after the queue entry is known.
@@ -164,7 +172,8 @@ namespace crb
             const uint32_t x = pix % rp.w, y = row_of(rp, pix / rp.w);
             const uint32_t sample = rp.first_sample + s;
             const uint32_t key    = path_key(rp.seed, x + y * rp.w, sample);
-            const float    fx = (float(x) + rnd(key, 0)) / float(rp.w), fy = (float(y) + rnd(key, 1)) / float(rp.h);    // renderer.cpp:260-263
+            const float    fx = (float(x) + rnd_dim(rp, key, x + y * rp.w, sample, 0)) / float(rp.w),
+                           fy = (float(y) + rnd_dim(rp, key, x + y * rp.w, sample, 1)) / float(rp.h);    // renderer.cpp:260-263
             const DCamera &c = sc.cam;
             V3             o, d;
             if (c.mode == 0)
@@ -430,7 +439,7 @@ namespace crb
                             {
                                 // renderer.cpp:92-98, sampling.h:168-172
                                 const uint32_t key = path_key(rp.seed, x + y * rp.w, sample);
-                                const V3       h   = sf.normal + sample_sphere(rnd(key, 2 + 4 * i), rnd(key, 2 + 4 * i + 1));
+                                const V3       h   = sf.normal + sample_sphere(rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i), rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i + 1));
                                 no                 = sf.point + sf.normal * 0.0001f;
                                 nd                 = normalize(h);
                             }
@@ -459,7 +468,7 @@ namespace crb
                                 // renderer.cpp:316-329,348-353; sampling.h:53-57,72-80
                                 const uint32_t key = path_key(rp.seed, x + y * rp.w, sample);
                                 const V3       so  = sf.point + sf.normal * 0.001f;
-                                const V3       l   = map_to_solid_angle(rnd(key, 2 + 4 * i + 2), rnd(key, 2 + 4 * i + 3), sc.sun.one_minus_cos);
+                                const V3       l   = map_to_solid_angle(rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i + 2), rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i + 3), sc.sun.one_minus_cos);
                                 const float   *T   = sc.sun.transform;
                                 const V3       dir = (v3(T[0], T[1], T[2]) * l.x + v3(T[3], T[4], T[5]) * l.y) + v3(T[6], T[7], T[8]) * l.z;
                                 const float    cosine    = clampf(dot(sf.normal, dir), 0.0f, 1.0f);
@@ -1109,6 +1118,7 @@ namespace crb
         RenderParams rp {};
         rp.w = w, rp.h = h, rp.row0 = row0, rp.nrows = nrows, rp.npix = npix, rp.seed = seed;
         rp.band = band, rp.band_first = band_first, rp.band_stride = band_stride;
+        rp.table = sample_table.p, rp.table_samples = sample_table.p ? table_samples : 0u, rp.table_dims = table_dims;
         rp.aov_sample = first + n - 1;
         rp.accum = accum.p, rp.display = display.p, rp.albedo = albedo.p, rp.normal = normal.p, rp.depth = depth.p;
 
@@ -1233,6 +1243,23 @@ namespace crb
 #else
         CRB_LAUNCH(k_resolve, (n + 255) / 256, 256, stream(), accum.p, display.p, n);
 #endif
+    }
+
+    void Render::set_sample_table(const float *table_host, uint32_t n_samples, uint32_t dims)
+    {
+        sync();
+        if (!table_host || !n_samples || !dims)
+        {
+            sample_table.release();
+            table_samples = table_dims = 0;
+            return;
+        }
+        if (flags & CRB_RENDER_FLAG_EXTENDED) throw Error(ERR_INVALID_ARG, "set_sample_table: the table layout is the ref-exact mode's (2 + 4 dimensions per bounce)");
+        const size_t n = size_t(n_samples) * w * h * dims;
+        sample_table.alloc(n);
+        dev_upload(sample_table.p, table_host, n * sizeof(float), stream());
+        stream_sync(stream());
+        table_samples = n_samples, table_dims = dims;
     }
 
     void Render::set_pass_count(uint32_t passes_)

@@ -49,6 +49,8 @@ namespace crb
         uint32_t bounce;
         uint32_t band, band_first, band_stride;    // band != 0: local rows are interleaved bands (tile partition), see row_of()
         float4  *accum, *display, *albedo, *normal, *depth;
+        const float *table;    // caller-supplied sample table [table_samples][w*h][table_dims] or nullptr
+        uint32_t     table_samples, table_dims;
     };
 
     struct Render
@@ -96,6 +98,8 @@ namespace crb
 #endif
         DBuf<float4> staging;
         uint64_t     next_ticket = 0;
+        DBuf<float>  sample_table;
+        uint32_t     table_samples = 0, table_dims = 0;
 #ifndef CRB_EMU
         // CRB_RENDER_FLAG_TIMERS: event pairs around every launch, resolved at sync()
         struct Timed
@@ -122,6 +126,7 @@ namespace crb
         void sync();
         void resolve();
         void set_pass_count(uint32_t passes_);
+        void set_sample_table(const float *table_host, uint32_t n_samples, uint32_t dims);
         void read(int kind, float *dst);
         uint64_t read_async(int kind, float *dst);
         void     read_wait(uint64_t ticket);

@@ -394,7 +394,7 @@ namespace crb
             return true;
         }
 
-        // cr::asset_loader::load_model (asset_loader.cpp:182-303). Polygons are fan-triangulated (what tinyobj does for
+        // cr::asset_loader::load_model (asset_loader.cpp:182-303). Quads are split along the shorter diagonal, larger polygons fan-triangulated (what tinyobj does for
         // convex faces). Faces without a material get a default material appended (tinyobj reports id -1, which the
         // reference would use to index materials[] out of bounds).
         inline model_data load_model(const std::string &file, std::string folder = std::string())
@@ -492,11 +492,33 @@ namespace crb
                         }
                         corners.push_back({ v > 0 ? v - 1 : int64_t(md.vertices.size()) + v, t ? (t > 0 ? t - 1 : int64_t(md.texture_coords.size()) + t) : -1 });
                     }
-                    for (size_t k = 1; k + 1 < corners.size(); k++)
-                    {
-                        for (const auto &cc : { corners[0], corners[k], corners[k + 1] }) md.vertex_indices.push_back(uint32_t(cc.first)), ti.push_back(cc.second);
+                    auto emit = [&](size_t a, size_t b, size_t c3) {
+                        for (const auto &cc : { corners[a], corners[b], corners[c3] }) md.vertex_indices.push_back(uint32_t(cc.first)), ti.push_back(cc.second);
                         mi.push_back(cur);
+                    };
+                    bool quad_done = false;
+                    if (corners.size() == 4)
+                    {
+                        // tinyobj (the reference's vendored loader, external/tinyobj/tinobj.h:1394-1490) splits a quad along
+                        // its SHORTER diagonal, in float: |v2-v0|^2 < |v3-v1|^2 -> (0,1,2)(0,2,3), else (0,1,3)(1,2,3)
+                        bool in_range = true;
+                        for (const auto &cc : corners) in_range = in_range && cc.first >= 0 && size_t(cc.first) < md.vertices.size();
+                        if (in_range)
+                        {
+                            const vec3 &p0 = md.vertices[size_t(corners[0].first)], &p1 = md.vertices[size_t(corners[1].first)], &p2 = md.vertices[size_t(corners[2].first)],
+                                       &p3 = md.vertices[size_t(corners[3].first)];
+                            const float ax = p2[0] - p0[0], ay = p2[1] - p0[1], az = p2[2] - p0[2], bx = p3[0] - p1[0], by = p3[1] - p1[1], bz = p3[2] - p1[2];
+                            const float sqr02 = ax * ax + ay * ay + az * az, sqr13 = bx * bx + by * by + bz * bz;
+                            if (sqr02 < sqr13)
+                                emit(0, 1, 2), emit(0, 2, 3);
+                            else
+                                emit(0, 1, 3), emit(1, 2, 3);
+                            quad_done = true;
+                        }
                     }
+                    // larger polygons: a fan, which is what tinyobj's ear clipping produces for convex faces
+                    if (!quad_done)
+                        for (size_t k = 1; k + 1 < corners.size(); k++) emit(0, k, k + 1);
                 }
             }
             std::map<std::string, uint32_t> already;
@@ -627,6 +649,180 @@ namespace crb
             return write_file(path, f);
         }
 
+        // Baseline JPEG (ITU-T T.81) writer for export_framebuffer(JPG): the reference calls stbi_write_jpg(path, w, h, 4,
+        // data, 100) (asset_loader.cpp:103-109), i.e. quality 100: every quantiser step is 1, no chroma subsampling,
+        // Y/Cb/Cr from RGB (alpha ignored), 8x8 forward DCT, the standard's example Huffman tables (Annex K.3). This is an
+        // own implementation of the standard; decoded pixels agree with the reference's file to within rounding
+        // (tests/test_reference_anchor.py compares both through the reference's own decoder).
+        namespace detail
+        {
+            struct jpeg_bits
+            {
+                std::vector<uint8_t> &out;
+                uint32_t              acc = 0;
+                int                   n   = 0;
+                void put(uint32_t code, int len)
+                {
+                    acc = (acc << len) | (code & ((1u << len) - 1u));
+                    n += len;
+                    while (n >= 8)
+                    {
+                        const uint8_t b = uint8_t(acc >> (n - 8));
+                        out.push_back(b);
+                        if (b == 0xff) out.push_back(0);    // byte stuffing
+                        n -= 8;
+                    }
+                }
+                void flush()
+                {
+                    if (n) put(0x7f, 8 - n);    // pad with ones
+                }
+            };
+            struct jpeg_huff
+            {
+                uint16_t code[256];
+                uint8_t  len[256];
+                jpeg_huff(const uint8_t *bits /*16*/, const uint8_t *vals)
+                {
+                    for (int i = 0; i < 256; i++) code[i] = 0, len[i] = 0;
+                    uint16_t c = 0;
+                    int      k = 0;
+                    for (int l = 1; l <= 16; l++)
+                    {
+                        for (int i = 0; i < bits[l - 1]; i++, k++) code[vals[k]] = c++, len[vals[k]] = uint8_t(l);
+                        c <<= 1;
+                    }
+                }
+            };
+            inline void jpeg_fdct8x8(float *b)
+            {
+                // separable 8-point DCT-II, orthonormal scaling of T.81 A.3.3
+                static float C[8][8];
+                static bool  init = false;
+                if (!init)
+                {
+                    for (int u = 0; u < 8; u++)
+                        for (int x = 0; x < 8; x++) C[u][x] = float((u == 0 ? std::sqrt(0.125) : 0.5) * std::cos((2 * x + 1) * u * M_PI / 16.0));
+                    init = true;
+                }
+                float t[64];
+                for (int y = 0; y < 8; y++)
+                    for (int u = 0; u < 8; u++)
+                    {
+                        float s = 0;
+                        for (int x = 0; x < 8; x++) s += C[u][x] * b[y * 8 + x];
+                        t[y * 8 + u] = s;
+                    }
+                for (int v = 0; v < 8; v++)
+                    for (int u = 0; u < 8; u++)
+                    {
+                        float s = 0;
+                        for (int y = 0; y < 8; y++) s += C[v][y] * t[y * 8 + u];
+                        b[v * 8 + u] = s;
+                    }
+            }
+        }    // namespace detail
+
+        inline bool export_jpg(const std::string &path, const float *rgba, uint32_t w, uint32_t h)
+        {
+            using namespace detail;
+            static const uint8_t zz[64] = { 0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                            35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+            // Annex K.3 tables
+            static const uint8_t dc_l_bits[16] = { 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0 }, dc_c_bits[16] = { 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0 };
+            static const uint8_t dc_vals[12]   = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 };
+            static const uint8_t ac_l_bits[16] = { 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d }, ac_c_bits[16] = { 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77 };
+            static const uint8_t ac_l_vals[162] = {
+                0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71, 0x14, 0x32, 0x81, 0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1,
+                0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16, 0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37,
+                0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a,
+                0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3,
+                0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3,
+                0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa
+            };
+            static const uint8_t ac_c_vals[162] = {
+                0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22, 0x32, 0x81, 0x08, 0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1,
+                0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36,
+                0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69,
+                0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a,
+                0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca,
+                0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa
+            };
+            const jpeg_huff hdc[2] = { jpeg_huff(dc_l_bits, dc_vals), jpeg_huff(dc_c_bits, dc_vals) };
+            const jpeg_huff hac[2] = { jpeg_huff(ac_l_bits, ac_l_vals), jpeg_huff(ac_c_bits, ac_c_vals) };
+
+            std::vector<uint8_t> f { 0xff, 0xd8, 0xff, 0xe0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0 };
+            for (int t = 0; t < 2; t++)    // two quantisation tables, every step 1 (quality 100)
+            {
+                f.insert(f.end(), { 0xff, 0xdb, 0, 67, uint8_t(t) });
+                f.insert(f.end(), 64, 1);
+            }
+            f.insert(f.end(), { 0xff, 0xc0, 0, 17, 8, uint8_t(h >> 8), uint8_t(h), uint8_t(w >> 8), uint8_t(w), 3, 1, 0x11, 0, 2, 0x11, 1, 3, 0x11, 1 });
+            auto dht = [&](int cls_id, const uint8_t *bits, const uint8_t *vals, int nvals) {
+                f.insert(f.end(), { 0xff, 0xc4, uint8_t((19 + nvals) >> 8), uint8_t(19 + nvals), uint8_t(cls_id) });
+                f.insert(f.end(), bits, bits + 16);
+                f.insert(f.end(), vals, vals + nvals);
+            };
+            dht(0x00, dc_l_bits, dc_vals, 12), dht(0x10, ac_l_bits, ac_l_vals, 162), dht(0x01, dc_c_bits, dc_vals, 12), dht(0x11, ac_c_bits, ac_c_vals, 162);
+            f.insert(f.end(), { 0xff, 0xda, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0 });
+
+            jpeg_bits bw { f };
+            int       pred[3] = { 0, 0, 0 };
+            for (uint32_t by = 0; by < h; by += 8)
+                for (uint32_t bx = 0; bx < w; bx += 8)
+                {
+                    float blk[3][64];
+                    for (int y = 0; y < 8; y++)
+                        for (int x = 0; x < 8; x++)
+                        {
+                            const uint32_t px = std::min(bx + uint32_t(x), w - 1), py = std::min(by + uint32_t(y), h - 1);    // edge replication
+                            const float   *p  = rgba + (size_t(py) * w + px) * 4;
+                            const float    r = to_byte(p[0]), g = to_byte(p[1]), b = to_byte(p[2]);
+                            blk[0][y * 8 + x] = 0.299f * r + 0.587f * g + 0.114f * b - 128.0f;
+                            blk[1][y * 8 + x] = -0.168736f * r - 0.331264f * g + 0.5f * b;
+                            blk[2][y * 8 + x] = 0.5f * r - 0.418688f * g - 0.081312f * b;
+                        }
+                    for (int c = 0; c < 3; c++)
+                    {
+                        jpeg_fdct8x8(blk[c]);
+                        int q[64];
+                        for (int i = 0; i < 64; i++) q[i] = int(std::lround(blk[c][zz[i]]));
+                        const int t = c ? 1 : 0;
+                        auto      mag = [](int v, int &bits) {
+                            int a = v < 0 ? -v : v, n = 0;
+                            while (a) n++, a >>= 1;
+                            bits = v < 0 ? v - 1 : v;
+                            return n;
+                        };
+                        int       bits;
+                        const int diff = q[0] - pred[c];
+                        pred[c]        = q[0];
+                        int n          = mag(diff, bits);
+                        bw.put(hdc[t].code[n], hdc[t].len[n]);
+                        if (n) bw.put(uint32_t(bits), n);
+                        int run = 0, last = 63;
+                        while (last > 0 && q[last] == 0) last--;
+                        for (int i = 1; i <= last; i++)
+                        {
+                            if (q[i] == 0)
+                            {
+                                run++;
+                                continue;
+                            }
+                            while (run > 15) bw.put(hac[t].code[0xf0], hac[t].len[0xf0]), run -= 16;
+                            n = mag(q[i], bits);
+                            bw.put(hac[t].code[(run << 4) | n], hac[t].len[(run << 4) | n]);
+                            bw.put(uint32_t(bits), n);
+                            run = 0;
+                        }
+                        if (last != 63) bw.put(hac[t].code[0], hac[t].len[0]);    // EOB
+                    }
+                }
+            bw.flush();
+            f.push_back(0xff), f.push_back(0xd9);
+            return write_file(path, f);
+        }
+
         // cr::asset_loader::export_framebuffer (asset_loader.cpp:348-377): writes out_dir/name.ext, or "name (n).ext"
         // when that exists; returns the file written
         inline std::string export_framebuffer(const image &buffer, const std::string &name, image_type type, const std::string &out_dir = "./out/")
@@ -643,7 +839,7 @@ namespace crb
             case image_type::PNG: ok = export_png(target, buffer.data.data(), w, h); break;
             case image_type::HDR: ok = export_hdr(target, buffer.data.data(), w, h); break;
             case image_type::EXR: ok = export_exr(target, buffer.data.data(), w, h); break;
-            default: throw error(CRB_ERR_INVALID_ARG, "JPG export is provided by the Python host (crender_b200.assets) only");
+            case image_type::JPG: ok = export_jpg(target, buffer.data.data(), w, h); break;
             }
             if (!ok) throw error(CRB_ERR_GENERIC, ("cannot write " + target).c_str());
             return target;

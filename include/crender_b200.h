@@ -225,6 +225,13 @@ int crb_render_read(crb_render *, int kind, float *dst_host);
 int crb_render_read_async(crb_render *, int kind, float *dst_host, uint64_t *ticket);
 int crb_render_read_wait(crb_render *, uint64_t ticket);
 int crb_render_stats(crb_render *, crb_stats *out); /* renderer::current_stats, renderer.cpp:396-404 */
+/* The reference draws its random numbers from a default-seeded thread_local std::mt19937 in call order
+ * (renderer.cpp:6-11); the library's default is a counter-based hash of (seed, pixel, sample, dimension). A caller-supplied
+ * table replaces the hash: table[(sample * w*h + pixel) * dims + d], pixel = x + y*w in sample space, dimensions 0,1 =
+ * pixel jitter, 2+4i+{0,1} = scatter of bounce i, 2+4i+{2,3} = sun sample of bounce i (ref-exact mode only; samples or
+ * dimensions beyond the table fall back to the hash). Uses: low-discrepancy sequences, and replaying the reference's own
+ * stream so that an image can be compared with the reference's (tests/test_reference_anchor.py). NULL removes it. */
+int crb_render_set_sample_table(crb_render *, const float *table_host, uint32_t n_samples, uint32_t dims);
 /* checkpoint / resume (the reference restarts from 0 spp on every start(), renderer.cpp:154-170): a
  * CRB_RAW_SUM read is a complete checkpoint; restore uploads it (w*h*4 floats) with its pass count, after
  * which crb_render_samples(first_sample = passes, ...) continues the same progressive render bit for bit */

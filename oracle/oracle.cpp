@@ -684,7 +684,8 @@ namespace
 
     // renderer.cpp:21-102. u0,u1 are the two scatter draws (consumed by smooth; drawn and
     // discarded by metal; not drawn by glass).
-    processed_hit process_hit(const record &rec, const ray &r, const scene &sc, float u0, float u1)
+    template<typename Draw2>
+    processed_hit process_hit_d(const record &rec, const ray &r, const scene &sc, Draw2 &&draw2)
     {
         processed_hit       out;
         const orc_material &mat = *rec.material;
@@ -724,12 +725,15 @@ namespace
         case ORC_METAL:
         {
             out.r.origin    = rec.point + rec.normal * 0.0001f;
+            (void) draw2();    // renderer.cpp:81: hemp_cos(record.normal, vec2(randf(), randf())) is computed and never used
             out.r.direction = reflect(r.direction, rec.normal);
             out.albedo      = out.albedo * mat.reflectiveness;
             break;
         }
         default:    // smooth
         {
+            const vec2 uu   = draw2();
+            const float u0 = uu.x, u1 = uu.y;
             const vec3 h    = hemp_cos(rec.normal, u0, u1);
             out.r.origin    = rec.point + rec.normal * 0.0001f;
             out.r.direction = normalize(h);
@@ -737,6 +741,11 @@ namespace
         }
         }
         return out;
+    }
+
+    inline processed_hit process_hit(const record &rec, const ray &r, const scene &sc, float u0, float u1)
+    {
+        return process_hit_d(rec, r, sc, [&] { return vec2 { u0, u1 }; });
     }
 
     // sampling.h:53-57
@@ -883,6 +892,39 @@ namespace
         std::vector<float> buffer, normals, albedo, depth;     // renderer.h:87-91 RGBA f32
         uint32_t           current_sample = 0;
         std::atomic<uint64_t> total_queries { 0 }, ref_rays { 0 }, pixel_samples { 0 };
+        // sampler_mode 1 = the REFERENCE's own stream (renderer.cpp:6-11): one default-seeded std::mt19937 consumed in call
+        // order by a single worker thread. Used only to compare this restatement with the reference's sources compiled
+        // under oracle/ref (tests/test_reference_anchor.py); needs nthreads == 1. Where the reference leaves the order
+        // of two randf() calls to the compiler (function / constructor arguments), the order is the one g++ produces:
+        // right to left, i.e. the SECOND argument gets the first draw.
+        int          sampler_mode = 0;
+        std::mt19937 mt;
+        // sample table: in reference-stream mode the draws that feed the estimator are recorded by (sample, pixel,
+        // dimension) — dimensions as in the counter-based sampler: 0,1 jitter; 2+4i+{0,1} scatter of bounce i;
+        // 2+4i+{2,3} sun sample of bounce i — so that the CUDA path can replay the reference's own numbers
+        // (crb_render_set_sample_table). sampler_mode 2 reads the same table back.
+        float   *table      = nullptr;
+        uint32_t table_dims = 0, table_samples = 0;
+        vec2     table_pair(uint32_t sample, uint64_t pixel, uint32_t dim, vec2 drawn)
+        {
+            if (!table || dim + 1 >= table_dims || sample >= table_samples) return drawn;
+            float *e = table + (size_t(sample) * w * h + pixel) * table_dims + dim;
+            if (sampler_mode == 2) return vec2 { e[0], e[1] };
+            e[0] = drawn.x, e[1] = drawn.y;
+            return drawn;
+        }
+        float        mt_randf()
+        {
+            std::uniform_real_distribution<float> dist(0.f, 1.f);
+            return dist(mt);
+        }
+        vec2 mt_pair()
+        {
+            vec2 p;
+            p.y = mt_randf();
+            p.x = mt_randf();
+            return p;
+        }
         bool                    extended = false;    // see "EXTENDED shading mode" above
         bool                    light_nee = true;    // false: leave the light list empty (emitters found by hits only; estimator cross-check)
         std::vector<area_light> lights;              // emissive triangles in world space, (model, instance, triangle) order
@@ -915,7 +957,14 @@ namespace
         void sample_pixel(uint64_t x, uint64_t y, uint32_t sample, uint64_t &queries, uint64_t &fired, record *primary_out)
         {
             const uint32_t key = path_key(seed, uint32_t(x + y * w), sample);
-            ray r = sc->cam.get_ray((float(x) + rnd(key, 0)) / float(uint64_t(w)), (float(y) + rnd(key, 1)) / float(uint64_t(h)), aspect);
+            const bool     ref_stream = sampler_mode == 1;
+            const uint64_t pixel      = x + y * w;
+            auto           draw       = [&](uint32_t dim) {
+                const vec2 d = ref_stream ? mt_pair() : vec2 { rnd(key, dim), rnd(key, dim + 1) };
+                return sampler_mode ? table_pair(sample, pixel, dim, d) : d;
+            };
+            const vec2 jit = draw(0);
+            ray r = sc->cam.get_ray((float(x) + jit.x) / float(uint64_t(w)), (float(y) + jit.y) / float(uint64_t(h)), aspect);
 
             vec3  throughput = V3(1, 1, 1), final = V3(0, 0, 0), albedo_ = V3(0, 0, 0), normal_ = V3(0, 0, 0);
             float depth_     = 0.0f;
@@ -942,7 +991,7 @@ namespace
                 }
                 else
                 {
-                    ph = process_hit(isect, r, *sc, rnd(key, 2 + 4 * i), rnd(key, 2 + 4 * i + 1));
+                    ph = process_hit_d(isect, r, *sc, [&] { return draw(2 + 4 * i); });
                     if (ph.is_alpha)
                     {
                         r.origin = isect.point + r.direction * 0.1f;
@@ -958,7 +1007,8 @@ namespace
                 {
                     ray out_ray { isect.point + isect.normal * 0.001f, V3(0, 0, 0) };
                     // sampling.h:72-80
-                    const vec3  dir    = mul(sc->sun_transform, map_to_solid_angle(rnd(key, 2 + 4 * i + 2), rnd(key, 2 + 4 * i + 3), sc->sun.size));
+                    const vec2  su     = draw(2 + 4 * i + 2);
+                    const vec3  dir    = mul(sc->sun_transform, map_to_solid_angle(su.x, su.y, sc->sun.size));
                     const float pdf    = solid_angle_mapping_pdf(sc->sun.size);
                     const float cosine = clampf(dot(isect.normal, dir), 0.0f, 1.0f);
                     out_ray.direction  = dir;
@@ -967,14 +1017,16 @@ namespace
                     queries++;
                     if (sun_isect.distance != INF)
                     {
-                        processed_hit pi = process_hit(sun_isect, r, *sc, 0.5f, 0.5f);    // draws unused
+                        // process_hit on the occluder draws (and discards) two numbers for metal / smooth (renderer.cpp:81,93)
+                        auto          waste = [&] { return ref_stream ? mt_pair() : vec2 { 0.5f, 0.5f }; };
+                        processed_hit pi    = process_hit_d(sun_isect, r, *sc, waste);
                         while (sun_isect.distance != INF && pi.is_alpha)
                         {
                             out_ray.origin = sun_isect.point + out_ray.direction * 0.1f;
                             sun_isect      = sc->cast_ray(out_ray);
                             queries++;
                             if (sun_isect.distance == INF) break;
-                            pi = process_hit(sun_isect, r, *sc, 0.5f, 0.5f);
+                            pi = process_hit_d(sun_isect, r, *sc, waste);
                         }
                     }
                     if (sun_isect.distance == INF)
@@ -1344,6 +1396,43 @@ void        orc_render_reset(orc_render *r) { r->r.reset(); }
 void        orc_render_set_extended(orc_render *r, int on) { r->r.extended = on != 0, r->r.light_nee = on != 2; }
 void        orc_render_set_rows(orc_render *r, uint32_t y0, uint32_t y1) { r->r.row0 = y0, r->r.row1 = std::min(y1, r->r.h); }
 void        orc_render_samples(orc_render *r, uint32_t first, uint32_t n, int nthreads) { r->r.run(first, n, nthreads); }
+
+void orc_render_set_sample_table(orc_render *r, float *table, uint32_t n_samples, uint32_t dims, int replay)
+{
+    r->r.table = table, r->r.table_samples = n_samples, r->r.table_dims = dims;
+    if (replay) r->r.sampler_mode = 2;
+}
+
+void orc_render_set_reference_stream(orc_render *r, int on, uint64_t discard)
+{
+    r->r.sampler_mode = on ? 1 : 0;
+    r->r.mt           = std::mt19937();    // default seed 5489, like `thread_local std::mt19937 gen;`
+    r->r.mt.discard(discard);
+}
+
+// ---- the bare BVH + triangle test (stands in for the Embree scene of ONE model): used by oracle/ref's embree3 shim
+struct orc_rawbvh
+{
+    model m;
+};
+orc_rawbvh *orc_rawbvh_create(const float *verts9, uint32_t ntris)
+{
+    orc_rawbvh *b = new orc_rawbvh();
+    b->m.ntris    = ntris;
+    b->m.verts.resize(size_t(ntris) * 3);
+    if (ntris) std::memcpy(static_cast<void *>(b->m.verts.data()), verts9, sizeof(float) * 9 * size_t(ntris));
+    b->m.build();
+    return b;
+}
+void orc_rawbvh_destroy(orc_rawbvh *b) { delete b; }
+int  orc_rawbvh_intersect(const orc_rawbvh *b, const float *o, const float *d, float tnear, float tfar, float *t, float *u, float *v, uint32_t *prim)
+{
+    tri_hit h;
+    b->m.intersect(V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), tnear, tfar, h);
+    if (h.prim == 0xffffffffu) return 0;
+    *t = h.t, *u = h.u, *v = h.v, *prim = h.prim;
+    return 1;
+}
 
 void orc_render_read(orc_render *r, int kind, float *dst)
 {

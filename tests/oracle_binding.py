@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
     L.orc_kat_scatter_extended.restype = C.c_int
     L.orc_kat_scatter_extended.argtypes = [C.POINTER(OMaterial), P, P, P, C.c_float, C.c_float, P, P, P]
     L.orc_render_set_rows.argtypes = [P, C.c_uint32, C.c_uint32]
+    L.orc_render_set_reference_stream.argtypes = [P, C.c_int, C.c_uint64]
+    L.orc_render_set_sample_table.argtypes = [P, P, C.c_uint32, C.c_uint32, C.c_int]
     L.orc_render_samples.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int]
     L.orc_render_read.argtypes = [P, C.c_int, P]
     L.orc_render_stats.argtypes = [P, C.POINTER(OStats)]
@@ -209,6 +211,16 @@ class renderer:
 
     def set_rows(self, y0, y1):
         self._L.orc_render_set_rows(self._h, y0, y1)
+
+    def set_reference_stream(self, on=True, discard=0):
+        """The reference's own default-seeded mt19937 consumed in call order by one thread (render with nthreads=1)."""
+        self._L.orc_render_set_reference_stream(self._h, int(on), int(discard))
+
+    def set_sample_table(self, table, replay=False):
+        """table: float32 [n_samples, h*w, dims], kept alive by this object. Recorded in reference-stream mode, or replayed."""
+        assert table.dtype == np.float32 and table.flags["C_CONTIGUOUS"] and table.ndim == 3
+        self._table = table
+        self._L.orc_render_set_sample_table(self._h, _ptr(table), table.shape[0], table.shape[2], int(replay))
 
     def render(self, n_spp, first_sample=None, nthreads=None):
         first = self._next if first_sample is None else first_sample

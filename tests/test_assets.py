@@ -42,9 +42,10 @@ def test_load_model(tmp_path):
     md = assets.load_model(str(tmp_path / "test.obj"))
     assert md.name == "test"
     assert md.vertices.shape == (5, 3) and md.texture_coords.shape == (4, 2)
-    # the quad is fan-triangulated: (1,2,3) (1,3,4), then the triangle
-    np.testing.assert_array_equal(md.vertex_indices, [0, 1, 2, 0, 2, 3, 1, 4, 2])
-    np.testing.assert_array_equal(md.texture_indices, [0, 1, 2, 0, 2, 3, 1, 0, 2])
+    # the quad is split like the reference's vendored tinyobj does (shorter diagonal; a square's equal diagonals give
+    # (0,1,3) (1,2,3) — verified against the compiled reference in test_reference_anchor.py), then the triangle
+    np.testing.assert_array_equal(md.vertex_indices, [0, 1, 3, 1, 2, 3, 1, 4, 2])
+    np.testing.assert_array_equal(md.texture_indices, [0, 1, 3, 1, 2, 3, 1, 0, 2])
     np.testing.assert_array_equal(md.material_indices, [0, 0, 1])
     assert [m.name for m in md.materials] == ["red", "tex"]
     assert tuple(md.materials[0].colour) == (0.8, 0.1, 0.2, 1.0) and md.materials[0].shade_type == 1 and md.materials[0].emission == 0.0
