@@ -101,6 +101,7 @@ SIGNATURES = {
     "crb_scene_set_skybox": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_float, C.c_float]),
     "crb_scene_set_camera": (C.c_int, [_P, C.POINTER(Camera)]),
     "crb_scene_commit": (C.c_int, [_P, C.POINTER(BuildInfo)]),
+    "crb_scene_set_option": (C.c_int, [_P, C.c_int, C.c_int]),
     "crb_intersect_batch": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
     "crb_occluded_batch": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
     "crb_trace_counters": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

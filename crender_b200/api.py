@@ -196,6 +196,11 @@ class scene:
         cc = _capi.Camera((C.c_float * 3)(*cam.position), (C.c_float * 3)(*cam.rotation), cam.fov, cam.scale, cam.current_mode)
         _capi.check(self._lib, self._lib.crb_scene_set_camera(self._h, C.byref(cc)))
 
+    def set_flatten_instances(self, on: bool):
+        """Instanced scenes: expand the instances into world-space triangles under one BVH (the fast path) instead of
+        the default two-level traversal that reproduces the reference's per-instance arithmetic bit for bit."""
+        _capi.check(self._lib, self._lib.crb_scene_set_option(self._h, 1, int(bool(on))))
+
     def commit(self) -> _capi.BuildInfo:
         info = _capi.BuildInfo()
         _capi.check(self._lib, self._lib.crb_scene_commit(self._h, C.byref(info)))

@@ -194,6 +194,13 @@ int crb_scene_set_camera(crb_scene *s, const crb_camera *c)
         s->s.version++;
     });
 }
+int crb_scene_set_option(crb_scene *s, int option, int value)
+{
+    return on_scene(s, [&](crb::Scene &sc) {
+        if (option != CRB_SCENE_OPT_FLATTEN_INSTANCES) throw crb::Error(crb::ERR_INVALID_ARG, "set_option: unknown option");
+        if (sc.flatten_instances != (value != 0)) sc.flatten_instances = value != 0, sc.committed = false, sc.version++, sc.geom_version++;
+    });
+}
 int crb_scene_commit(crb_scene *s, crb_build_info *info)
 {
     return on_scene(s, [&](crb::Scene &) {
@@ -205,7 +212,7 @@ int crb_scene_commit(crb_scene *s, crb_build_info *info)
             info->n_triangles = s->s.build.n_tris;
             info->n_nodes     = s->s.build.n_nodes;
             info->node_bytes  = uint64_t(s->s.build.n_nodes) * 80;
-            info->tri_bytes   = uint64_t(s->s.build.n_tris) * 48;
+            info->tri_bytes   = uint64_t(s->s.stored_tris) * 48 + (s->s.two_level ? uint64_t(s->s.n_instances) * (sizeof(crb::Instance) + 48) : 0);
             info->max_depth   = s->s.build.max_depth;
             info->sah_cost    = s->s.build.sah_cost;
         }

@@ -146,7 +146,26 @@ namespace crb
             return __ldg(px + (x + y * w));
         }
 
-        __device__ __forceinline__ uint32_t src_tri(const DScene &sc, uint32_t flat) { return sc.flat_src ? __ldg(sc.flat_src + flat) : flat; }
+        // the (model, instance) range that holds a flat primitive id (two-level mode: range index = instance index)
+        __device__ __forceinline__ uint32_t range_of(const DScene &sc, uint32_t flat)
+        {
+            uint32_t lo = 0, hi = sc.n_ranges;
+            while (hi - lo > 1)
+            {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(&sc.ranges[mid].start) <= flat) lo = mid; else hi = mid;
+            }
+            return lo;
+        }
+        __device__ __forceinline__ uint32_t src_tri(const DScene &sc, uint32_t flat)
+        {
+            if (sc.two_level)
+            {
+                const FlatRange r = sc.ranges[range_of(sc, flat)];
+                return r.src_start + (flat - r.start);
+            }
+            return sc.flat_src ? __ldg(sc.flat_src + flat) : flat;
+        }
 
         // local row r of this render call -> frame row y in sample space: a contiguous range [row0, row0+nrows), or the
         // interleaved bands of the tile partition (band rows each, every band_stride-th band starting at band_first):
@@ -290,15 +309,33 @@ namespace crb
             float    uvx, uvy;
         };
 
-        __device__ __forceinline__ Surface surface_at(const DScene &sc, V3 o, V3 dn, float4 hit)
+        // o, d: the cr::ray as the reference holds it (direction not re-normalised). model.cpp:107-120: per instance the ray is
+        // taken to object space with the inverse transform, the direction renormalised, the hit point mapped back with the
+        // transform and the distance re-measured in world space. Single-level scenes (identity instances) reduce to
+        // point = o + normalize(d) * t.
+        __device__ __forceinline__ Surface surface_at(const DScene &sc, V3 o, V3 d, float4 hit)
         {
             Surface        s;
-            const uint32_t src = src_tri(sc, __float_as_uint(hit.w));
-            const float4   st  = __ldg(sc.shade_tri + src);
-            s.normal           = v3(st.x, st.y, st.z);
-            s.mat              = __float_as_uint(st.w);
-            s.point            = o + dn * hit.x;            // ray.at(tfar), ray.cpp:13-16
-            s.distance         = length(s.point - o);       // glm::distance
+            const uint32_t flat = __float_as_uint(hit.w);
+            uint32_t       src;
+            if (sc.two_level)
+            {
+                const uint32_t  k = range_of(sc, flat);
+                const FlatRange r = sc.ranges[k];
+                src               = r.src_start + (flat - r.start);
+                const Instance &I = sc.bvh2.inst[k];
+                const V3        oo = xf34(I.inv, o, 1.0f), dd = normalize(xf34(I.inv, d, 0.0f));
+                s.point            = xf34(I.fwd, oo + dd * hit.x, 1.0f);
+            }
+            else
+            {
+                src     = sc.flat_src ? __ldg(sc.flat_src + flat) : flat;
+                s.point = o + normalize(d) * hit.x;    // ray.at(tfar), ray.cpp:13-16
+            }
+            const float4 st = __ldg(sc.shade_tri + src);
+            s.normal        = v3(st.x, st.y, st.z);
+            s.mat           = __float_as_uint(st.w);
+            s.distance      = length(s.point - o);       // glm::distance
             s.uvx = s.uvy = 0.f;
             if (sc.obj_uvs)
             {
@@ -398,7 +435,7 @@ namespace crb
                     else
                     {
                         const V3         dn  = normalize(d);
-                        const Surface    sf  = surface_at(sc, o, dn, h4);
+                        const Surface    sf  = surface_at(sc, o, d, h4);
                         const DMaterial  mat = sc.materials[sf.mat];
                         const float4     col = surface_colour(sc, mat, sf);
                         if (col.w == 0.0f)
@@ -598,7 +635,7 @@ namespace crb
                     }
                     else
                     {
-                        const Surface   sf  = surface_at(sc, o, dn, h4);
+                        const Surface   sf  = surface_at(sc, o, d, h4);
                         const DMaterial mat = sc.materials[sf.mat];
                         const float4    col = surface_colour(sc, mat, sf);
                         if (col.w == 0.0f)
@@ -752,6 +789,80 @@ namespace crb
             }
         }
 
+        // scene::cast_ray for ONE ray (the alpha cut-out shadow march): the flat BVH, or — two-level scenes — the reference's
+        // own loop over (model, instance) pairs (scene.cpp:79-98, model.cpp:99-126), nearest by re-measured world distance
+        template<bool COUNT>
+        __device__ __forceinline__ Hit cast_closest(const DScene &sc, V3 o, V3 d, V3 dn, TravCounters *tc)
+        {
+            if (!sc.two_level) return traverse<false, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), tc);
+            Hit   best { inf_f(), 0.f, 0.f, INVALID_PRIM };
+            float best_dist = inf_f();
+            for (uint32_t k = 0; k < sc.bvh2.n_inst; k++)
+            {
+                const Instance &I  = sc.bvh2.inst[k];
+                const V3        oo = xf34(I.inv, o, 1.0f), dd = normalize(xf34(I.inv, d, 0.0f));
+                const Blas      bl = sc.bvh2.blas[I.blas];
+                const Bvh8      view { sc.bvh2.nodes + size_t(bl.node_base) * 5, sc.bvh2.tris + size_t(bl.tri_base) * 3, bl.n_nodes, bl.n_tris };
+                const Hit       h = traverse<false, COUNT>(view, oo, dd, 0.00001f, inf_f(), tc);
+                if (h.prim == INVALID_PRIM) continue;
+                const float dist = length(xf34(I.fwd, oo + dd * h.t, 1.0f) - o);
+                if (dist < best_dist) best = Hit { h.t, h.u, h.v, I.flat_start + h.prim }, best_dist = dist;
+            }
+            return best;
+        }
+
+        // ------------------------------------------------------------------ two-level variants of the two traversal kernels
+        template<bool COUNT>
+        __global__ void __launch_bounds__(256, 3) k_trace2(DScene sc, PathState ps)
+        {
+            const uint32_t n = ps.counters[CTR_IN];
+            TravCounters   tc;
+            auto source = [&](uint32_t idx, uint32_t &slot, V3 &o, V3 &d, float &tmin, float &tmax) {
+                slot            = ps.q_in[idx];
+                const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);    // as the reference holds it: every instance renormalises (model.cpp:110-112)
+                tmin = 0.00001f, tmax = inf_f();
+            };
+            auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
+                if (valid) ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            };
+            trace_persistent_2l<COUNT, TRACE_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_TRACE, n, false, source, sink, &tc);
+            if (COUNT)
+            {
+                atomicAdd(ps.stats + ST_NODES, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS, tc.tris);
+            }
+        }
+
+        template<bool COUNT>
+        __global__ void __launch_bounds__(256, 3) k_shadow2(DScene sc, PathState ps)
+        {
+            const uint32_t n = ps.counters[CTR_SHADOW];
+            TravCounters   tc;
+            auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
+                item            = idx;
+                const float4 so = ps.shadow[idx].o, sd = ps.shadow[idx].d;
+                o = v3(so.x, so.y, so.z), d = v3(sd.x, sd.y, sd.z);
+                tmin = 0.00001f, tmax = sd.w;    // inf for the sun, 0.999 * distance (world) for an area light
+            };
+            auto sink = [&](bool valid, uint32_t item, const Hit &h) {
+                if (valid && h.prim == INVALID_PRIM)
+                {
+                    const uint32_t slot = __float_as_uint(ps.shadow[item].o.w);
+                    const float4   c    = ps.shadow[item].c;
+                    const float4   r4   = ps.rad[slot];
+                    const V3       r    = v3(r4.x, r4.y, r4.z) + v3(c.x, c.y, c.z);
+                    ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
+                }
+            };
+            trace_persistent_2l<COUNT, TRACE_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_SHADOW, n, true, source, sink, &tc);
+            if (COUNT)
+            {
+                atomicAdd(ps.stats + ST_NODES_SHADOW, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS_SHADOW, tc.tris);
+            }
+        }
+
         // ------------------------------------------------------------------ K8 shadow rays
         // sun visibility without alpha cut-outs: any-hit through the persistent trace loop
         template<bool COUNT, int STEPS>
@@ -806,13 +917,13 @@ namespace crb
                     float           remaining = sr.d.w;    // inf for the sun (the reference's loop), finite for area lights (extended mode)
                     for (int guard = 0; guard < 4096; guard++)
                     {
-                        const Hit h = traverse<false, COUNT>(sc.bvh, o, dn, 0.00001f, inf_f(), &tc);
+                        const Hit h = cast_closest<COUNT>(sc, o, d, dn, &tc);
                         if (h.prim == INVALID_PRIM)
                         {
                             visible = true;
                             break;
                         }
-                        const Surface   sf  = surface_at(sc, o, dn, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
+                        const Surface   sf  = surface_at(sc, o, d, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
                         if (!(sf.distance <= remaining))
                         {
                             visible = true;
@@ -1125,9 +1236,9 @@ namespace crb
         const bool count = (flags & CRB_RENDER_FLAG_COUNTERS) != 0;
         static const int steps = getenv("CRB_TRACE_STEPS") ? atoi(getenv("CRB_TRACE_STEPS")) : TRACE_STEPS;    // tuning knob
 #ifdef CRB_EMU
-        const unsigned pgrid = 1, pblock = 1, tgrid = 1, sgrid = 1, sblock = 1;
+        const unsigned pgrid = 1, pblock = 1, tgrid = 1, t2grid = 1, sgrid = 1, sblock = 1;
 #else
-        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC,
+        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC, t2grid = unsigned(n_sms) * 3,
                        sgrid = unsigned(n_sms) * (1024 / CRB_SHADE_BLOCK), sblock = CRB_SHADE_BLOCK;
         const Span span { take_event(), take_event() };
         CRB_CUDA_CHECK(cudaEventRecord(span.a, stream()));
@@ -1156,7 +1267,14 @@ namespace crb
             {
                 rp.bounce = i;
                 tick(CRB_K_TRACE);
-                if (count)
+                if (dscene.two_level)
+                {
+                    if (count)
+                        CRB_LAUNCH((k_trace2<true>), t2grid, pblock, st, dscene, ps);
+                    else
+                        CRB_LAUNCH((k_trace2<false>), t2grid, pblock, st, dscene, ps);
+                }
+                else if (count)
                     CRB_LAUNCH((k_trace<true, TRACE_STEPS>), tgrid, pblock, st, dscene, ps);
                 else if (steps == 1)
                     CRB_LAUNCH((k_trace<false, 1>), tgrid, pblock, st, dscene, ps);
@@ -1184,6 +1302,13 @@ namespace crb
                             CRB_LAUNCH((k_shadow_alpha<true>), pgrid, pblock, st, dscene, ps);
                         else
                             CRB_LAUNCH((k_shadow_alpha<false>), pgrid, pblock, st, dscene, ps);
+                    }
+                    else if (dscene.two_level)
+                    {
+                        if (count)
+                            CRB_LAUNCH((k_shadow2<true>), t2grid, pblock, st, dscene, ps);
+                        else
+                            CRB_LAUNCH((k_shadow2<false>), t2grid, pblock, st, dscene, ps);
                     }
                     else if (count)
                         CRB_LAUNCH((k_shadow<true, TRACE_STEPS>), tgrid, pblock, st, dscene, ps);

@@ -117,7 +117,9 @@ namespace crb
     int Scene::add_mesh(const float *verts, const float *uvs, const uint32_t *mat_idx, uint32_t ntris)
     {
         if (!verts && ntris) throw Error(ERR_BUILD_VERTS, "add_mesh: null vertex buffer");
+        static uint64_t next_geom_id = 1;
         HostModel m;
+        m.geom_id = next_geom_id++;
         m.ntris = ntris;
         host_copy(m.verts, verts, size_t(ntris) * 9);
         if (uvs) host_copy(m.uvs, uvs, size_t(ntris) * 6);
@@ -245,8 +247,230 @@ namespace crb
         version++;
     }
 
+    namespace
+    {
+        // glm::inverse(mat4) (model.cpp:109), glm 0.9.9.8 func_matrix.inl compute_inverse<4,4>, float, column-major m[c*4+r];
+        // compiled with -ffp-contract=off: one rounding per operation, the same bits as the reference's per-ray inverse
+        void glm_inverse(const float *M, float *out)
+        {
+            const auto m = [&](int c, int r) { return M[c * 4 + r]; };
+            const float Coef00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3), Coef02 = m(1, 2) * m(3, 3) - m(3, 2) * m(1, 3), Coef03 = m(1, 2) * m(2, 3) - m(2, 2) * m(1, 3);
+            const float Coef04 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3), Coef06 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3), Coef07 = m(1, 1) * m(2, 3) - m(2, 1) * m(1, 3);
+            const float Coef08 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2), Coef10 = m(1, 1) * m(3, 2) - m(3, 1) * m(1, 2), Coef11 = m(1, 1) * m(2, 2) - m(2, 1) * m(1, 2);
+            const float Coef12 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3), Coef14 = m(1, 0) * m(3, 3) - m(3, 0) * m(1, 3), Coef15 = m(1, 0) * m(2, 3) - m(2, 0) * m(1, 3);
+            const float Coef16 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2), Coef18 = m(1, 0) * m(3, 2) - m(3, 0) * m(1, 2), Coef19 = m(1, 0) * m(2, 2) - m(2, 0) * m(1, 2);
+            const float Coef20 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1), Coef22 = m(1, 0) * m(3, 1) - m(3, 0) * m(1, 1), Coef23 = m(1, 0) * m(2, 1) - m(2, 0) * m(1, 1);
+            const float F[6][4] = { { Coef00, Coef00, Coef02, Coef03 }, { Coef04, Coef04, Coef06, Coef07 }, { Coef08, Coef08, Coef10, Coef11 },
+                                    { Coef12, Coef12, Coef14, Coef15 }, { Coef16, Coef16, Coef18, Coef19 }, { Coef20, Coef20, Coef22, Coef23 } };
+            const float V[4][4] = { { m(1, 0), m(0, 0), m(0, 0), m(0, 0) }, { m(1, 1), m(0, 1), m(0, 1), m(0, 1) }, { m(1, 2), m(0, 2), m(0, 2), m(0, 2) },
+                                    { m(1, 3), m(0, 3), m(0, 3), m(0, 3) } };
+            float       col[4][4];
+            const float sa[4] = { +1, -1, +1, -1 }, sb[4] = { -1, +1, -1, +1 };
+            for (int i = 0; i < 4; i++)
+            {
+                col[0][i] = ((V[1][i] * F[0][i] - V[2][i] * F[1][i]) + V[3][i] * F[2][i]) * sa[i];
+                col[1][i] = ((V[0][i] * F[0][i] - V[2][i] * F[3][i]) + V[3][i] * F[4][i]) * sb[i];
+                col[2][i] = ((V[0][i] * F[1][i] - V[1][i] * F[3][i]) + V[3][i] * F[5][i]) * sa[i];
+                col[3][i] = ((V[0][i] * F[2][i] - V[1][i] * F[4][i]) + V[2][i] * F[5][i]) * sb[i];
+            }
+            const float d0 = m(0, 0) * col[0][0], d1 = m(0, 1) * col[1][0], d2 = m(0, 2) * col[2][0], d3 = m(0, 3) * col[3][0];
+            const float inv_det = 1.0f / ((d0 + d1) + (d2 + d3));
+            for (int c = 0; c < 4; c++)
+                for (int r = 0; r < 4; r++) out[c * 4 + r] = col[c][r] * inv_det;
+        }
+    }    // namespace
+
+    // Two-level commit: one object-space BLAS per model (rebuilt only when the geometry set changed), a TLAS over the
+    // (model, instance) pairs (rebuilt on every commit: an instance edit costs a 10..100-instance build, not a rebuild of
+    // 18M flattened triangles), and the instance table with glm's inverse of every transform.
+    void Scene::commit_two_level()
+    {
+        auto t0 = std::chrono::steady_clock::now();
+        const int B = 256;
+        size_t n_src = 0, n_flat64 = 0;
+        bool   any_uv = false;
+        for (const HostModel &m : models) n_src += m.ntris, n_flat64 += size_t(m.ntris) * (m.transforms.size() / 16), any_uv = any_uv || !m.uvs.empty();
+        if (n_flat64 > 0x7ffffff0ull) throw Error(ERR_BUILD_INDEX, "scene exceeds 2^31 instanced triangles");
+        n_flat = uint32_t(n_flat64);
+        std::vector<uint64_t> ids;
+        for (const HostModel &m : models) ids.push_back(m.geom_id);
+        BuildOptions opt;
+        if (const char *e = getenv("CRB_TREELET_PASSES")) opt.treelet_passes = atoi(e);
+        if (const char *e = getenv("CRB_OPTIMAL_COLLAPSE")) opt.optimal_collapse = atoi(e) != 0;
+        if (const char *e = getenv("CRB_COST_PRIM")) opt.cost_prim = float(atof(e));
+        double upload = 0;
+
+        bool rebuilt = false;
+        if (ids != blas_geom_ids || !d_blas_nodes.p)
+        {
+            rebuilt = true;
+            // ---- geometry changed: upload object-space data, per-triangle shading records, one BLAS per model
+            DBuf<float>    d_obj_verts;
+            DBuf<uint32_t> d_mat_idx;
+            d_obj_verts.alloc(n_src * 9 + 1);
+            d_mat_idx.alloc(n_src + 1);
+            d_shade_tri.alloc(n_src + 1);
+            if (any_uv) d_obj_uvs.alloc(n_src * 6); else d_obj_uvs.release();
+            d_flat_src.release();
+            size_t   src_off = 0;
+            uint32_t mat_base = 0;
+            for (const HostModel &m : models)
+            {
+                dev_upload(d_obj_verts.p + src_off * 9, m.verts.data(), size_t(m.ntris) * 9 * 4, stream);
+                dev_upload(d_mat_idx.p + src_off, m.mat_idx.data(), size_t(m.ntris) * 4, stream);
+                if (any_uv)
+                {
+                    if (!m.uvs.empty())
+                        dev_upload(d_obj_uvs.p + src_off * 6, m.uvs.data(), size_t(m.ntris) * 6 * 4, stream);
+                    else
+                        dev_zero(d_obj_uvs.p + src_off * 6, size_t(m.ntris) * 6 * 4, stream);
+                }
+                if (m.ntris) CRB_LAUNCH(k_shade_tri, (m.ntris + B - 1) / B, B, stream, d_obj_verts.p + src_off * 9, d_mat_idx.p + src_off, mat_base, m.ntris, d_shade_tri.p + src_off);
+                src_off += m.ntris;
+                mat_base += uint32_t(m.materials.size());
+            }
+            stream_sync(stream);
+            upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            std::vector<DBuf<uint4>>  bn(models.size());
+            std::vector<DBuf<float4>> bt(models.size());
+            blas_table.assign(models.size(), Blas {});
+            blas_build_ms = 0, blas_nodes_total = 0, blas_depth = 0;
+            size_t   node_total = 0, tri_total = 0;
+            float    sah = 0;
+            src_off = 0;
+            for (size_t mi = 0; mi < models.size(); mi++)
+            {
+                BuildStats st;
+                build_bvh8(d_obj_verts.p + src_off * 9, models[mi].ntris, stream, opt, bn[mi], bt[mi], st);
+                blas_table[mi] = Blas { uint32_t(node_total), uint32_t(tri_total), st.n_nodes, st.n_tris };
+                node_total += st.n_nodes, tri_total += st.n_tris;
+                blas_build_ms += st.build_ms, blas_depth = std::max(blas_depth, st.max_depth), sah += st.sah_cost;
+                src_off += models[mi].ntris;
+            }
+            d_blas_nodes.alloc(node_total * 5 + 5);
+            d_blas_tris.alloc(tri_total * 3 + 3);
+            for (size_t mi = 0; mi < models.size(); mi++)
+            {
+                dev_copy(d_blas_nodes.p + size_t(blas_table[mi].node_base) * 5, bn[mi].p, size_t(blas_table[mi].n_nodes) * 80, stream);
+                dev_copy(d_blas_tris.p + size_t(blas_table[mi].tri_base) * 3, bt[mi].p, size_t(blas_table[mi].n_tris) * 48, stream);
+            }
+            d_blas.alloc(models.size() ? models.size() : 1);
+            dev_upload(d_blas.p, blas_table.data(), blas_table.size() * sizeof(Blas), stream);
+            stream_sync(stream);
+            blas_nodes_total = uint32_t(node_total);
+            build.sah_cost   = sah;
+            blas_geom_ids    = ids;
+        }
+        auto t1 = std::chrono::steady_clock::now();
+
+        // ---- instances: table, flat ranges, bounds, TLAS
+        ranges.clear();
+        std::vector<Instance> inst;
+        std::vector<float>    proxy;    // one "triangle" per instance whose box is the instance's bounds
+        size_t   src_off = 0, flat_off = 0;
+        for (size_t mi = 0; mi < models.size(); mi++)
+        {
+            const HostModel &m = models[mi];
+            // object-space bounds of the model (cached per geometry would save this O(T) host loop on instance edits; 2M: ~5 ms)
+            float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+            for (size_t i = 0; i < size_t(m.ntris) * 3; i++)
+                for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], m.verts[i * 3 + a]), hi[a] = std::max(hi[a], m.verts[i * 3 + a]);
+            const size_t ni = m.transforms.size() / 16;
+            for (size_t ii = 0; ii < ni && m.ntris; ii++)
+            {
+                const float *T = &m.transforms[16 * ii];
+                float        inv[16];
+                glm_inverse(T, inv);
+                Instance I {};
+                for (int c = 0; c < 4; c++)
+                    for (int r = 0; r < 3; r++) I.inv[3 * c + r] = inv[4 * c + r], I.fwd[3 * c + r] = T[4 * c + r];
+                float wlo[3] = { 3e38f, 3e38f, 3e38f }, whi[3] = { -3e38f, -3e38f, -3e38f };
+                for (int corner = 0; corner < 8; corner++)
+                {
+                    const double p[3] = { (corner & 1) ? hi[0] : lo[0], (corner & 2) ? hi[1] : lo[1], (corner & 4) ? hi[2] : lo[2] };
+                    for (int r = 0; r < 3; r++)
+                    {
+                        const double w = double(T[r]) * p[0] + double(T[4 + r]) * p[1] + double(T[8 + r]) * p[2] + double(T[12 + r]);
+                        wlo[r] = std::min(wlo[r], float(w)), whi[r] = std::max(whi[r], float(w));
+                    }
+                }
+                for (int r = 0; r < 3; r++)
+                {
+                    // the device maps hit points back in float: keep the box conservative by a few ulps of its size / position
+                    const float pad = 1e-5f * std::max(std::max(std::fabs(wlo[r]), std::fabs(whi[r])), whi[r] - wlo[r]) + 1e-30f;
+                    I.lo[r] = wlo[r] - pad, I.hi[r] = whi[r] + pad;
+                }
+                I.blas = uint32_t(mi), I.flat_start = uint32_t(flat_off);
+                inst.push_back(I);
+                proxy.insert(proxy.end(), { I.lo[0], I.lo[1], I.lo[2], I.hi[0], I.hi[1], I.hi[2], I.lo[0], I.hi[1], I.lo[2] });
+                FlatRange r {};
+                r.start = uint32_t(flat_off), r.ntris = m.ntris, r.model = uint32_t(mi), r.inst = uint32_t(ii), r.src_start = uint32_t(src_off);
+                ranges.push_back(r);
+                flat_off += m.ntris;
+            }
+            src_off += m.ntris;
+        }
+        n_flat = uint32_t(flat_off);
+        d_ranges.alloc(ranges.size() ? ranges.size() : 1);
+        dev_upload(d_ranges.p, ranges.data(), ranges.size() * sizeof(FlatRange), stream);
+        d_inst.alloc(inst.size() ? inst.size() : 1);
+        dev_upload(d_inst.p, inst.data(), inst.size() * sizeof(Instance), stream);
+        DBuf<float> d_proxy;
+        d_proxy.alloc(proxy.size() + 9);
+        dev_upload(d_proxy.p, proxy.data(), proxy.size() * 4, stream);
+        // ---- textures, materials, skybox (as in the flat path)
+        {
+            std::vector<DTexture> dt;
+            size_t                total = 0;
+            for (const HostTexture &t : textures)
+            {
+                dt.push_back(DTexture { t.w, t.h, uint32_t(total), 0 });
+                total += size_t(t.w) * t.h;
+            }
+            d_textures.alloc(dt.size() ? dt.size() : 1);
+            d_texels.alloc(total ? total : 1);
+            dev_upload(d_textures.p, dt.data(), dt.size() * sizeof(DTexture), stream);
+            for (size_t i = 0; i < textures.size(); i++) dev_upload(d_texels.p + dt[i].offset, textures[i].rgba.data(), textures[i].rgba.size() * 4, stream);
+        }
+        upload_materials();
+        if (sky_w && sky_h && !d_skybox.p) upload_skybox();
+        stream_sync(stream);
+        upload_ms = upload + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+        BuildStats tl;
+        build_bvh8(d_proxy.p, uint32_t(inst.size()), stream, opt, d_nodes, d_tris, tl);
+        tlas_build_ms   = tl.build_ms;
+        build.build_ms  = tl.build_ms + (rebuilt ? blas_build_ms : 0.0);    // an instance edit pays for the TLAS only
+        stored_tris     = 0;
+        for (const Blas &b : blas_table) stored_tris += b.n_tris;
+        build.n_nodes   = tl.n_nodes + blas_nodes_total;
+        build.n_tris    = n_flat;
+        build.max_depth = tl.max_depth + blas_depth;
+        tlas_nodes      = tl.n_nodes;
+        n_instances     = uint32_t(inst.size());
+        two_level       = true;
+        committed       = true;
+        version++;
+    }
+
     void Scene::commit()
     {
+        {
+            // instanced scenes trace through a TLAS with the reference's per-instance arithmetic (bit-identical hits);
+            // flattening into world space stays as the fast path behind crb_scene_set_option / CRB_FLATTEN=1
+            bool instanced = false;
+            for (const HostModel &m : models)
+                instanced = instanced || m.transforms.size() != 16 || !is_identity16(m.transforms.data());
+            static const int flatten_env = getenv("CRB_FLATTEN") ? atoi(getenv("CRB_FLATTEN")) : -1;
+            const bool       flatten     = flatten_env >= 0 ? flatten_env != 0 : flatten_instances;
+            if (instanced && !flatten)
+            {
+                commit_two_level();
+                return;
+            }
+            two_level = false;
+            blas_geom_ids.clear();
+            d_blas_nodes.release(), d_blas_tris.release();
+        }
         auto t0 = std::chrono::steady_clock::now();
         // ---- sizes
         size_t n_src = 0, n_flat64 = 0;
@@ -342,6 +566,7 @@ namespace crb
         if (const char *e = getenv("CRB_OPTIMAL_COLLAPSE")) opt.optimal_collapse = atoi(e) != 0;
         if (const char *e = getenv("CRB_COST_PRIM")) opt.cost_prim = float(atof(e));
         build_bvh8(d_wverts.p, n_flat, stream, opt, d_nodes, d_tris, build);
+        stored_tris = build.n_tris;
         d_wverts.release();
         committed = true;
         version++;
@@ -360,7 +585,7 @@ namespace crb
 
     void Scene::copy_light_state_from(const Scene &src)
     {
-        sun = src.sun, sun_enabled = src.sun_enabled, camera = src.camera;
+        sun = src.sun, sun_enabled = src.sun_enabled, camera = src.camera, flatten_instances = src.flatten_instances;
         sky_rot[0] = src.sky_rot[0], sky_rot[1] = src.sky_rot[1];
         if (src_sky_version != src.sky_version)
         {
@@ -396,6 +621,12 @@ namespace crb
         d.ranges = d_ranges.p, d.n_ranges = uint32_t(ranges.size());
         d.has_alpha = has_alpha ? 1u : 0u;
         d.lights = d_lights.p, d.n_lights = n_lights;
+        d.two_level = two_level ? 1u : 0u;
+        if (two_level)
+        {
+            d.bvh2.tlas.nodes = d_nodes.p, d.bvh2.tlas.tris = d_tris.p, d.bvh2.tlas.n_nodes = tlas_nodes, d.bvh2.tlas.n_tris = n_instances;
+            d.bvh2.nodes = d_blas_nodes.p, d.bvh2.tris = d_blas_tris.p, d.bvh2.blas = d_blas.p, d.bvh2.inst = d_inst.p, d.bvh2.n_inst = n_instances;
+        }
 
         // ---- sun: registry.cpp:248-256 + sampling.h:21-47 (host libm, same as the reference's CPU)
         DSun &s = d.sun;

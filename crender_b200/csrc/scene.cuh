@@ -63,7 +63,7 @@ namespace crb
         uint32_t enabled;
     };
 
-    struct FlatRange    // flat primitive ids [start, start+ntris) belong to (model, inst)
+    struct FlatRange    // flat primitive ids [start, start+ntris) belong to (model, inst); in two-level mode range k = Instance k
     {
         uint32_t start, ntris, model, inst, src_start, pad[3];
     };
@@ -84,6 +84,8 @@ namespace crb
         const FlatRange *ranges;
         uint32_t        n_ranges;
         uint32_t        has_alpha;    // any material that can produce colour.w == 0
+        Bvh2            bvh2;         // two-level mode: TLAS over instances + one object-space BLAS per model (bvh8.cuh)
+        uint32_t        two_level;    // 1: trace through bvh2 with the reference's per-instance arithmetic; 0: bvh (flat)
         const float4   *lights;       // extended mode: 3 per emissive world-space triangle: (v0, Le.r) (e1, Le.g) (e2, Le.b)
         uint32_t        n_lights;
         DSun            sun;
@@ -180,6 +182,7 @@ namespace crb
 
     struct HostModel
     {
+        uint64_t                  geom_id = 0;    // unique per add_mesh: tells commit() which BLASes are still valid
         uint32_t                  ntris = 0;
         HostVec<float>            verts, uvs;
         HostVec<uint32_t>         mat_idx;
@@ -223,8 +226,20 @@ namespace crb
         DBuf<FlatRange>  d_ranges;
         DBuf<float4>     d_lights;         // emissive triangles for the extended mode's area-light NEE
         uint32_t         n_lights = 0;
-        DBuf<uint4>      d_nodes;
+        DBuf<uint4>      d_nodes;          // flat mode: the one BVH; two-level mode: the TLAS
         DBuf<float4>     d_tris;
+        // two-level mode (instanced scenes unless flatten_instances): BLASes survive instance edits
+        bool             flatten_instances = false;    // crb_scene_set_option(CRB_SCENE_OPT_FLATTEN_INSTANCES): the r1 fast path
+        bool             two_level = false;
+        DBuf<uint4>      d_blas_nodes;
+        DBuf<float4>     d_blas_tris;
+        DBuf<Blas>       d_blas;
+        DBuf<Instance>   d_inst;
+        std::vector<uint64_t> blas_geom_ids;           // geometry the BLAS set was built from
+        std::vector<Blas>     blas_table;
+        double           blas_build_ms = 0, tlas_build_ms = 0;
+        uint32_t         blas_nodes_total = 0, blas_depth = 0, tlas_nodes = 0, n_instances = 0;
+        uint64_t         stored_tris = 0;    // triangles actually resident (two-level: every model once)
         std::vector<FlatRange> ranges;
         BuildStats       build;
         double           upload_ms = 0;
@@ -239,6 +254,7 @@ namespace crb
         void set_instances(int model, const float *mats, uint32_t n);
         int  add_texture(const float *rgba, uint32_t w, uint32_t h);
         void commit();
+        void commit_two_level();
         void upload_materials();    // also recomputes has_alpha and the light list
         void upload_skybox();
         DScene device_scene(uint32_t w, uint32_t h) const;    // camera aspect from the render target

@@ -74,6 +74,39 @@ namespace crb
             }
         }
 
+        // two-level scenes: the ray parameter t is invariant under the instance's affine map (no renormalisation for a
+        // batch query with the caller's tnear/tfar), candidates are compared by t, ties go to the first (model, instance)
+        template<bool COUNT, bool ANY>
+        __global__ void __launch_bounds__(256, 3) k_batch2(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits, uint8_t *__restrict__ occ,
+                                                         uint32_t *cursor, unsigned long long *ctr)
+        {
+            TravCounters tc;
+            auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
+                item           = idx;
+                const float4 a = rays[2 * size_t(idx)], b = rays[2 * size_t(idx) + 1];
+                o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z), tmin = a.w, tmax = b.w;
+            };
+            auto sink = [&](bool valid, uint32_t item, const Hit &h) {
+                if (COUNT || !valid) return;
+                if (ANY)
+                {
+                    if (occ) occ[item] = h.prim != INVALID_PRIM ? 1 : 0;
+                    return;
+                }
+                crb_hit out;
+                out.t = h.t, out.u = h.u, out.v = h.v;
+                out.prim = INVALID_PRIM, out.model = INVALID_PRIM, out.inst = 0;
+                if (h.prim != INVALID_PRIM) resolve_flat(sc, h.prim, out.prim, out.model, out.inst);
+                hits[item] = out;
+            };
+            trace_persistent_2l<COUNT, BATCH_STEPS, false>(sc.bvh2, cursor, n, ANY, source, sink, &tc);
+            if (COUNT)
+            {
+                atomicAdd(ctr + 0, tc.nodes);
+                atomicAdd(ctr + 1, tc.tris);
+            }
+        }
+
         struct Timer
         {
 #ifndef CRB_EMU
@@ -117,6 +150,22 @@ namespace crb
             const unsigned g = unsigned(s.n_sms) * 4, blk = 256;
 #endif
             dev_zero(cursor, 4, st);
+            if (sc.two_level)
+            {
+#ifdef CRB_EMU
+                const unsigned g2 = 1;
+#else
+                const unsigned g2 = unsigned(s.n_sms) * 3;
+#endif
+                switch (mode)
+                {
+                case 0: CRB_LAUNCH((k_batch2<false, false>), g2, blk, st, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), (uint8_t *) nullptr, cursor, ctr); break;
+                case 1: CRB_LAUNCH((k_batch2<false, true>), g2, blk, st, sc, rp, cnt32, (crb_hit *) nullptr, reinterpret_cast<uint8_t *>(op), cursor, ctr); break;
+                case 2: CRB_LAUNCH((k_batch2<true, false>), g2, blk, st, sc, rp, cnt32, (crb_hit *) nullptr, (uint8_t *) nullptr, cursor, ctr); break;
+                default: CRB_LAUNCH((k_batch2<true, true>), g2, blk, st, sc, rp, cnt32, (crb_hit *) nullptr, (uint8_t *) nullptr, cursor, ctr); break;
+                }
+                return;
+            }
             switch (mode)
             {
             case 0: CRB_LAUNCH((k_intersect_batch<false>), g, blk, st, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), cursor, ctr); break;

@@ -99,7 +99,7 @@ typedef struct crb_build_info
 {
     double   build_ms;  /* device time of the BVH build (the rtcCommitScene replacement) */
     double   upload_ms; /* host->device copies + flattening */
-    uint64_t n_triangles; /* flattened world-space triangles (instances expanded) */
+    uint64_t n_triangles; /* triangles a ray can hit: instances expanded (resident only once per model in two-level scenes) */
     uint64_t n_nodes;     /* 8-wide nodes */
     uint64_t node_bytes;
     uint64_t tri_bytes;
@@ -168,9 +168,18 @@ int crb_scene_set_sun(crb_scene *, const crb_sun *sun_or_null, int enabled);
 int crb_scene_set_skybox(crb_scene *, const float *rgba, uint32_t w, uint32_t h, float rot_u, float rot_v);
 /* whole-struct camera assignment (src/ui/ui.h:674-675) */
 int crb_scene_set_camera(crb_scene *, const crb_camera *);
-/* model::instance_geometry -> rtcCommitGeometry/rtcAttachGeometry/rtcCommitScene
- * (src/objects/model.cpp:52-97): flatten instances, build the 8-wide BVH on the device. */
+/* model::instance_geometry -> rtcCommitGeometry/rtcAttachGeometry/rtcCommitScene (src/objects/model.cpp:52-97): builds
+ * the 8-wide BVH(s) on the device. A scene whose models all have the single identity instance gets one BVH. An instanced
+ * scene gets one object-space BVH per model + a top-level BVH over the (model, instance) pairs, and rays are taken into
+ * object space per instance with the reference's own arithmetic (glm::inverse of the transform, renormalised direction,
+ * hit point mapped back, distance re-measured: model.cpp:107-120) — hits are bit-identical to the reference's loop, every
+ * model is stored once, and an instance edit (crb_scene_set_instances + commit) rebuilds only the top level.
+ * CRB_SCENE_OPT_FLATTEN_INSTANCES = 1 selects the alternative: instances expanded into world-space triangles under ONE
+ * BVH (faster traversal on heavily overlapping instances, I x the memory, hits equal to the reference only up to the
+ * rounding of the changed coordinate frame, every instance edit is a full rebuild). */
 int crb_scene_commit(crb_scene *, crb_build_info *info_or_null);
+enum { CRB_SCENE_OPT_FLATTEN_INSTANCES = 1 };
+int crb_scene_set_option(crb_scene *, int option, int value);
 
 /* ---- queries: scene::cast_ray -> model::intersect -> rtcIntersect1 (scene.cpp:79-98,
  * model.cpp:5-49,99-126). rays/hits are host pointers unless on_device != 0. */

@@ -115,31 +115,42 @@ namespace
             }
         return R;
     }
-    // general 4x4 inverse by cofactors (what glm::inverse(mat4) computes, model.cpp:109)
+    // glm::inverse(mat4) (model.cpp:109) = glm 0.9.9.8 func_matrix.inl compute_inverse<4,4>: 18 2x2 sub-determinants
+    // (Coef..), six factor vectors, four cofactor columns with alternating signs, determinant from the first row. The
+    // operation order is glm's, so that a general (scaled / sheared) instance transform inverts to the same bits.
     mat4 inverse(const mat4 &M)
     {
-        const float *m = &M.m[0][0];
-        float        inv[16];
-        inv[0]  = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
-        inv[4]  = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
-        inv[8]  = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
-        inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
-        inv[1]  = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
-        inv[5]  = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
-        inv[9]  = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
-        inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
-        inv[2]  = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
-        inv[6]  = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
-        inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
-        inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
-        inv[3]  = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
-        inv[7]  = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
-        inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
-        inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
-        float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
-        float id  = 1.0f / det;
-        mat4  R;
-        for (int i = 0; i < 16; i++) (&R.m[0][0])[i] = inv[i] * id;
+        const auto m = [&](int c, int r) { return M.m[c][r]; };
+        const float Coef00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3), Coef02 = m(1, 2) * m(3, 3) - m(3, 2) * m(1, 3), Coef03 = m(1, 2) * m(2, 3) - m(2, 2) * m(1, 3);
+        const float Coef04 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3), Coef06 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3), Coef07 = m(1, 1) * m(2, 3) - m(2, 1) * m(1, 3);
+        const float Coef08 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2), Coef10 = m(1, 1) * m(3, 2) - m(3, 1) * m(1, 2), Coef11 = m(1, 1) * m(2, 2) - m(2, 1) * m(1, 2);
+        const float Coef12 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3), Coef14 = m(1, 0) * m(3, 3) - m(3, 0) * m(1, 3), Coef15 = m(1, 0) * m(2, 3) - m(2, 0) * m(1, 3);
+        const float Coef16 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2), Coef18 = m(1, 0) * m(3, 2) - m(3, 0) * m(1, 2), Coef19 = m(1, 0) * m(2, 2) - m(2, 0) * m(1, 2);
+        const float Coef20 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1), Coef22 = m(1, 0) * m(3, 1) - m(3, 0) * m(1, 1), Coef23 = m(1, 0) * m(2, 1) - m(2, 0) * m(1, 1);
+        struct v4
+        {
+            float x, y, z, w;
+        };
+        const auto mul4 = [](v4 a, v4 b) { return v4 { a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w }; };
+        const auto sub4 = [](v4 a, v4 b) { return v4 { a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w }; };
+        const auto add4 = [](v4 a, v4 b) { return v4 { a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w }; };
+        const v4 Fac0 { Coef00, Coef00, Coef02, Coef03 }, Fac1 { Coef04, Coef04, Coef06, Coef07 }, Fac2 { Coef08, Coef08, Coef10, Coef11 };
+        const v4 Fac3 { Coef12, Coef12, Coef14, Coef15 }, Fac4 { Coef16, Coef16, Coef18, Coef19 }, Fac5 { Coef20, Coef20, Coef22, Coef23 };
+        const v4 Vec0 { m(1, 0), m(0, 0), m(0, 0), m(0, 0) }, Vec1 { m(1, 1), m(0, 1), m(0, 1), m(0, 1) };
+        const v4 Vec2 { m(1, 2), m(0, 2), m(0, 2), m(0, 2) }, Vec3 { m(1, 3), m(0, 3), m(0, 3), m(0, 3) };
+        const v4 Inv0 = add4(sub4(mul4(Vec1, Fac0), mul4(Vec2, Fac1)), mul4(Vec3, Fac2));
+        const v4 Inv1 = add4(sub4(mul4(Vec0, Fac0), mul4(Vec2, Fac3)), mul4(Vec3, Fac4));
+        const v4 Inv2 = add4(sub4(mul4(Vec0, Fac1), mul4(Vec1, Fac3)), mul4(Vec3, Fac5));
+        const v4 Inv3 = add4(sub4(mul4(Vec0, Fac2), mul4(Vec1, Fac4)), mul4(Vec2, Fac5));
+        const v4 SignA { +1, -1, +1, -1 }, SignB { -1, +1, -1, +1 };
+        const v4 col[4] = { mul4(Inv0, SignA), mul4(Inv1, SignB), mul4(Inv2, SignA), mul4(Inv3, SignB) };
+        const v4 Dot0 { m(0, 0) * col[0].x, m(0, 1) * col[1].x, m(0, 2) * col[2].x, m(0, 3) * col[3].x };
+        const float Dot1 = (Dot0.x + Dot0.y) + (Dot0.z + Dot0.w);
+        const float OneOverDeterminant = 1.0f / Dot1;
+        mat4 R;
+        for (int c = 0; c < 4; c++)
+            R.m[c][0] = col[c].x * OneOverDeterminant, R.m[c][1] = col[c].y * OneOverDeterminant, R.m[c][2] = col[c].z * OneOverDeterminant,
+            R.m[c][3] = col[c].w * OneOverDeterminant;
         return R;
     }
     inline bool is_identity(const mat4 &M)

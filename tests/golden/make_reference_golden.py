@@ -34,6 +34,7 @@ CASES = {
     "cornell_rotated": (48, 32, 5, 3),
     "cornell_ortho": (48, 32, 5, 3),
     "mesh_sky": (48, 28, 6, 3),
+    "general_instances": (64, 48, 6, 4),
 }
 
 
@@ -50,6 +51,20 @@ def scene_of(name):
         d = scenes.mesh_scene(60, 30, sun_enabled=False)  # lit by an environment map only
         d.skybox = np.random.RandomState(9).uniform(0.0, 2.0, (8, 16, 4)).astype(np.float32)
         d.skybox_rotation = (0.2, 0.1)
+        return d
+    if name == "general_instances":
+        # instance transforms that are not rigid: non-uniform scale, rotation about a skew axis, shear (exercises
+        # glm::inverse's full cofactor arithmetic, the per-instance renormalisation and the world-space re-measuring of
+        # model.cpp:107-120)
+        d = scenes.textured_scene()
+        rs = np.random.RandomState(4)
+        inst = []
+        for k in range(4):
+            A = np.eye(4, dtype=np.float64)
+            A[:3, :3] = np.diag(rs.uniform(0.6, 1.6, 3)) @ np.linalg.qr(rs.normal(size=(3, 3)))[0] + rs.uniform(-0.15, 0.15, (3, 3))
+            A[:3, 3] = (rs.uniform(-1.5, 1.5), rs.uniform(0.2, 0.6), rs.uniform(0.8, 2.4))
+            inst.append(A.T.astype(np.float32))  # column-major storage m[c][r]
+        d.meshes[2].instances = np.stack(inst)
         return d
     return common.small_scenes()[name]
 

@@ -208,6 +208,10 @@ def test_update_semantics(oracle, product_lib):
     pc.check_update_semantics(oracle, product_lib)
 
 
+def test_instance_edits(oracle, product_lib):
+    pc.check_instance_edits(oracle, product_lib)
+
+
 def test_against_golden_fixtures(product_lib):
     """The CUDA path against the committed fixtures (no oracle at run time for this test)."""
     import os
@@ -225,9 +229,8 @@ def test_against_golden_fixtures(product_lib):
         g.commit()
         rays = common.mixed_rays(desc, make_golden.N_RAYS, seed=101)
         h = g.cast_rays(rays)
-        identity_only = all(m.instances is None for m in desc.meshes)
         same = (h["prim"] == gold[f"{name}/hit_prim"]) & (h["model"] == gold[f"{name}/hit_model"]) & (h["inst"] == gold[f"{name}/hit_inst"])
-        if identity_only:
+        if True:  # instanced scenes too: two-level traversal in the reference's own per-instance arithmetic
             assert same.all()
             np.testing.assert_array_equal(h["t"], gold[f"{name}/hit_t"])
             np.testing.assert_array_equal(h["u"], gold[f"{name}/hit_u"])
@@ -349,19 +352,31 @@ def config4(oracle, product_lib):
     return desc, g, o, info
 
 
-def test_config4_hits_vs_oracle(config4):
-    # the oracle intersects per instance in object space like the reference (model.cpp:99-126); the product traces the
-    # flattened world-space scene: ids agree on >= 99.99 %, t within 1e-5 relative + a few ulps of the coordinate size
+def test_config4_hits_vs_oracle(config4, product_lib):
+    # the oracle intersects per instance in object space like the reference (model.cpp:99-126), and so does the product's
+    # two-level traversal: 18 instances of 2M- and 768-triangle models, every hit record bit-identical
     desc, g, o, info = config4
     rays = common.mixed_rays(desc, 200000, seed=31)
     ho, hg = o.cast_rays(rays), g.cast_rays(rays)
+    assert (hg["prim"] != common.MISS).mean() > 0.2
+    for f in ("prim", "model", "inst", "t", "u", "v"):
+        np.testing.assert_array_equal(hg[f], ho[f], err_msg=f)
+    np.testing.assert_array_equal(g.occluded(rays).astype(bool), hg["prim"] != common.MISS)
+    # every model is resident once (two-level), not once per instance
+    assert info.tri_bytes < 0.2 * desc.n_flat_tris * 48
+    # the flattened alternative (one world-space BVH over 18M triangles): same surfaces, but a hit on a shared edge of the
+    # 2 mm terrain triangles can land on the neighbour when the coordinate frame changes — measured 99.985 % id agreement
+    gf = api.scene(lib_path=product_lib)
+    scenes.load(desc, gf)
+    gf.set_flatten_instances(True)
+    fi = gf.commit()
+    assert fi.tri_bytes == desc.n_flat_tris * 48
+    hf = gf.cast_rays(rays)
     lo, hi = desc.aabb()
     slack = 8 * float(np.finfo(np.float32).eps) * float(max(np.abs(lo).max(), np.abs(hi).max()) * 3.0)
-    agree, dt = common.hit_agreement(hg, ho, slack)
-    assert (hg["prim"] != common.MISS).mean() > 0.2
-    assert agree >= pc.PRIM_AGREE, agree
-    assert dt <= pc.T_REL, dt
-    np.testing.assert_array_equal(g.occluded(rays).astype(bool), hg["prim"] != common.MISS)
+    agree, dt = common.hit_agreement(hf, ho, slack)
+    assert agree >= 0.9995 and dt <= pc.T_REL, (agree, dt)
+    del gf
 
 
 def test_config4_rows_vs_oracle(oracle, config4):

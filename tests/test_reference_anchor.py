@@ -123,9 +123,9 @@ def product_vs_reference(oracle, gold, lib_path, name, exact):
 @pytest.mark.parametrize("name", list(mg.CASES))
 def test_kernel_logic_equals_reference(oracle, gold, emu_lib, name):
     # the product's kernel bodies (CPU harness, same libm as the reference build) replaying the reference's numbers:
-    # bit-identical images for scenes without instance transforms (instanced ones differ by the world-space flattening)
-    identity_only = all(m.instances is None for m in mg.scene_of(name).meshes)
-    product_vs_reference(oracle, gold, emu_lib, name, exact=identity_only)
+    # bit-identical images, AOVs and ray counts — instanced models included (two-level traversal with the reference's own
+    # per-instance arithmetic, incl. non-rigid transforms)
+    product_vs_reference(oracle, gold, emu_lib, name, exact=True)
 
 
 @pytest.mark.gpu

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box call (run through gpurun): tools/gpu_call.sh <tag> <what>...   what = smoke | tests | bench | benchq | ref | launches | ncu_trace | ncu_shade | multi
+# One GPU-box call (run through gpurun): tools/gpu_call.sh <tag> <what>...   what = smoke | tests | anchor | bench | benchq | ref | launches | ncu_trace | ncu_shade | multi
 # Everything lands under gpurun_out/<tag>_*; summaries for profiles/ are made afterwards in the development container
 # (tools/ncu_summary.py). Each step has its own timeout so that a hang cannot take the box.
 tag=$1; shift
@@ -9,6 +9,7 @@ for what in "$@"; do
   case $what in
     smoke)   ( time timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" ) > $out/${tag}_smoke.log 2>&1; tail -3 $out/${tag}_smoke.log ;;
     tests)   ( time timeout 1500 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest.log 2>&1; tail -8 $out/${tag}_pytest.log ;;
+    anchor)  ( time timeout 600 python -m pytest tests/test_reference_anchor.py -m gpu -x -q ) > $out/${tag}_pytest_anchor.log 2>&1; tail -4 $out/${tag}_pytest_anchor.log ;;
     bench)   timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 1500 $out/${tag}_bench.json; tail -3 $out/${tag}_bench.err ;;
     benchq)  timeout 300 python bench.py --no-cpu-baseline --no-configs > $out/${tag}_benchq.json 2> $out/${tag}_benchq.err; tail -c 1200 $out/${tag}_benchq.json; tail -3 $out/${tag}_benchq.err ;;
     ref)     timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err; tail -c 600 $out/${tag}_bench_ref.json ;;
