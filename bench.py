@@ -171,6 +171,32 @@ def oracle_render_rate(a, steps, warmup, seconds_budget=None):
     }
 
 
+def compiled_reference_rate(a, spp=2, timeout=180):
+    """The reference's OWN sources (renderer.cpp, scene.cpp, model.cpp, thread_pool.cpp ... compiled unmodified under
+    oracle/ref, Embree replaced by the oracle's BVH behind an embree3 shim) on the same scene, camera and resolution, all
+    host threads, `spp` full-frame passes. Prebuilt in the development container (oracle/_ref/ref_render travels with the
+    snapshot; /root/reference itself does not). None when the binary is absent or the reference dead-locks (it loses
+    condition-variable wake-ups, thread_pool.cpp:12-13,55-56)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import ref_binding as rb
+        from crender_b200 import scenes
+
+        if not os.path.exists(rb.REF_BIN):
+            return None
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        desc = scenes.mesh_scene(a.nu, a.nv)
+        pairs = sum(1 if m.instances is None else len(m.instances) for m in desc.meshes)
+        r = rb.render(desc, a.width, a.height, a.bounces, spp, binary=rb.REF_BIN, timeout=timeout, retries=2, threads=cores)
+        q = r["intersect_calls"] / pairs
+        return {"value": q / r["seconds"] / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{spp} full-frame passes of 1 spp at {a.width}x{a.height}, {cores} threads (the reference's own thread pool: one task per scanline)",
+                "samples_per_s": a.width * a.height * spp / r["seconds"], "ref_rays_per_s": r["total_rays"] / r["seconds"],
+                "note": "the reference's own renderer/scene/model/thread_pool sources compiled unmodified (oracle/ref); glm and Embree are shims, the BVH under rtcIntersect1 is the oracle's"}
+    except Exception as e:
+        return {"value": None, "kind": "reference", "failed": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -185,6 +211,7 @@ def run_reference(a):
         "cpu_baseline": {"value": res["mrays"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
         "e2e": {"value": res["mrays"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "samples_per_s": res["samples_per_s"], "bvh_build_ms": res["build_ms"],
+        "compiled_reference": compiled_reference_rate(a),
     }
     emit(line)
 
@@ -342,7 +369,8 @@ def run_ours(a):
             res = oracle_render_rate(a, 2, 1, seconds_budget=a.cpu_seconds)
             line["cpu_baseline"] = {"value": res["mrays"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"],
                                     "samples_per_s": res["samples_per_s"], "bvh_build_ms": res["build_ms"],
-                                    "note": "CRender-restated CPU oracle (own BVH) - Embree unavailable in image"}
+                                    "note": "CRender-restated CPU oracle (own BVH) - Embree unavailable in image",
+                                    "compiled_reference": compiled_reference_rate(a)}
         except Exception as e:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
@@ -522,12 +550,14 @@ def e2e_multi(a, ctx, r, step):
 
 
 # ---------------------------------------------------------------------------------------------- BASELINE configs 4 / 5 / 3
-def partitioned_config(a, ctx, api, scenes, D, desc, w, h, bounces, total_spp, n_steps, partition, extended, label, want_roofline):
+def partitioned_config(a, ctx, api, scenes, D, desc, w, h, bounces, total_spp, n_steps, partition, extended, label, want_roofline, flatten=False):
     """One multi-GPU workload at this N: scene + BVH replicated, `total_spp` passes in n_steps render calls whose sample
     range (spp) or row bands (tile) the library splits across the ranks, one merge per call on the side stream. Device
     time = CUDA events on the library's stream around all calls + the join of the last merge, max over ranks."""
     g = api.scene(device=ctx.local)
     scenes.load(desc, g)
+    if flatten:
+        g.set_flatten_instances(True)
     info = g.commit()
     kw = dict(seed=0, extended=extended)
     r = ctx.renderer(api, D, w, h, bounces, g, partition=partition, **kw)
@@ -546,6 +576,7 @@ def partitioned_config(a, ctx, api, scenes, D, desc, w, h, bounces, total_spp, n
         "ms_total": ms, "spp_total": per * n_steps, "spp_per_call": per, "calls": n_steps, "samples_per_s": ps / (ms * 1e-3), "rays_per_sample": q / max(1, ps),
         "passes_per_s": per * n_steps / (ms * 1e-3), "triangles": int(info.n_triangles), "bvh_bytes": int(info.node_bytes + info.tri_bytes),
         "bvh_build_ms": info.build_ms, "scene_upload_ms": info.upload_ms, "gpu_launches": int(launches), "merge": r.info()["merge"], "shading": "extended" if extended else "ref-exact",
+        "instances": "flattened into one world-space BVH" if flatten else "two-level (one BLAS per model + TLAS, the reference's per-instance arithmetic)",
     }
     # end to end: the same calls, wall clock, each followed by an asynchronous read of the merged display into pinned host memory
     outs = [ctx.pinned(h, w) for _ in range(2)]
@@ -578,7 +609,15 @@ def strong_c4(a, ctx, api, scenes, D):
     desc = scenes.terrain_city(1000, a.c4_grid)
     label = (f"config4: instanced terrain ({a.c4_grid}x{a.c4_grid} tiles of 2M triangles) + city = {desc.n_flat_tris} flattened triangles, 1920x1080, depth 8, "
              f"sun NEE, {a.c4_spp} spp split into contiguous sample ranges over the GPUs (spp partition), one merge per call")
-    return partitioned_config(a, ctx, api, scenes, D, desc, 1920, 1080, 8, a.c4_spp, 8, "spp", False, label, True)
+    out = partitioned_config(a, ctx, api, scenes, D, desc, 1920, 1080, 8, a.c4_spp, 8, "spp", False, label, True)
+    if ctx.world == 1:
+        # the flattened alternative (crb_scene_set_option): one 18M-triangle world-space BVH, 1 GB — the HBM-regime tree
+        try:
+            out["flattened"] = partitioned_config(a, ctx, api, scenes, D, desc, 1920, 1080, 8, min(a.c4_spp, 128), 2, "spp", False,
+                                                  label.split(",")[0] + f", flattened instances, {min(a.c4_spp, 128)} spp", True, flatten=True)
+        except Exception as e:
+            out["flattened"] = {"failed": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def tile_c5(a, ctx, api, scenes, D):
@@ -628,9 +667,20 @@ def c3_batch(a, ctx, api, scenes):
         rays[:, 0:3] = v / v.norm(dim=1, keepdim=True) * rad[:, None]
         return rays
 
+    def grazing_rays(cnt, occlusion):
+        # origins in the shell, directions TANGENT to the sphere (perpendicular to the radius): rays that skim the displaced
+        # surface for its whole length — the longest traversals this geometry offers
+        rays = shell_rays(cnt, occlusion)
+        radial = rays[:, 0:3] / rays[:, 0:3].norm(dim=1, keepdim=True)
+        dvec = rays[:, 4:7] - radial * (rays[:, 4:7] * radial).sum(dim=1, keepdim=True)
+        rays[:, 4:7] = dvec / dvec.norm(dim=1, keepdim=True).clamp_min(1e-6)
+        return rays
+
     out = {"workload": f"config3: {n} random-direction closest-hit + occlusion queries on the {int(info.n_triangles)}-triangle BVH", "triangles": int(info.n_triangles),
-           "bvh_bytes": int(info.node_bytes + info.tri_bytes)}
-    for name, maker in (("box", box_rays), ("shell", shell_rays)):
+           "bvh_bytes": int(info.node_bytes + info.tri_bytes),
+           "ray_sets": "box = the config's own (origins in the scene box inflated 1.5x, most rays miss the root); shell = origins inside the displaced surface's shell, "
+                       "uniform directions; grazing = shell origins, directions tangent to the sphere"}
+    for name, maker in (("box", box_rays), ("shell", shell_rays), ("grazing", grazing_rays)):
         sub = {}
         for any_hit, kind in ((False, "closest"), (True, "occluded")):
             rays = maker(n, any_hit)

@@ -282,7 +282,7 @@ namespace crb
     //
     // Incoherent rays have wildly different traversal lengths (a ray that misses the scene box needs one
     // node, a grazing ray 50+), so "one warp = 32 fixed rays" leaves most lanes idle while the longest ray
-    // finishes (measured: 6 of 32 lanes active per issued instruction, profiles/r1a_k_trace.md). Here a
+    // finishes (measured: 6 of 32 lanes active per issued instruction, round-1 history in DESIGN.md section 4). Here a
     // warp is a pool of 32 traversal lanes: whenever lanes are idle, the warp takes exactly that many new
     // work items from the global cursor with ONE atomic (warp-aggregated), and every lane keeps its own
     // traversal state in registers. Lanes reconverge every STEPS node iterations, where finished rays are
@@ -578,7 +578,7 @@ namespace crb
 // the scene stores every model once, and an instance edit rebuilds only the TLAS.
 namespace crb
 {
-    struct Instance    // 128 bytes
+    struct Instance    // 144 bytes = nine 16-byte loads
     {
         float    inv[12];    // object <- world: rows 0..2 of glm::inverse(transform), column-major: inv[3*c + r]
         float    fwd[12];    // world <- object: rows 0..2 of the transform
@@ -586,7 +586,9 @@ namespace crb
         uint32_t blas;       // model index
         float    hi[3];
         uint32_t flat_start; // flat primitive id of the instance's triangle 0 (FlatRange::start)
+        uint32_t node_base, tri_base, n_nodes, pad;    // the model's BLAS (copied from Blas: one dependent load less per entry)
     };
+    static_assert(sizeof(Instance) == 144, "Instance is read as nine float4");
     struct Blas
     {
         uint32_t node_base, tri_base, n_nodes, n_tris;
@@ -629,6 +631,15 @@ namespace crb
     //                   instance, u, v, flat prim } (the shader recomputes the world point like model.cpp:116-120).
     //   RENORM = false: batch queries (rtcIntersect1 with the caller's tnear/tfar): the ray parameter t is invariant
     //                   under the affine map, d is NOT renormalised, candidates are compared by t.
+    // Every iteration is a node phase (TLAS or BLAS nodes, one code path), a triangle phase (BLAS leaves) and an ENTRY
+    // phase in which lanes standing on a TLAS leaf take their ray into the instance's object space. The entry is ~150
+    // instructions (two matrix products, a normalisation, three reciprocals) and almost every iteration has SOME lane
+    // that wants it, so run eagerly it was paid per iteration at 1-3 active lanes (measured: k_trace2 1.74 against 3.48
+    // Grays/s for the flattened scene at equal node visits); it now runs when CRB_ENTRY_MIN lanes wait for it or nothing
+    // else in the warp can progress. The TLAS ray is kept per lane, so leaving an instance is a register move.
+#ifndef CRB_ENTRY_MIN
+#define CRB_ENTRY_MIN 6
+#endif
     template<bool COUNT, int STEPS, bool RENORM, typename Source, typename Sink>
     __device__ __forceinline__ void trace_persistent_2l(const Bvh2 &sc, uint32_t *cursor, uint32_t n, bool any, Source source, Sink sink, TravCounters *ctr)
     {
@@ -640,9 +651,11 @@ namespace crb
         bool     active = false, finished = false, exhausted = false, in_blas = false;
         uint32_t item = 0;
         V3       wo = v3(0, 0, 0), wd = v3(0, 0, 1);                     // the query as given (world)
+        V3       td = v3(0, 0, 1), tidir = v3(0, 0, 0);                  // the TLAS-level ray (unit direction when RENORM)
+        unsigned toct = 0;
         V3       o = v3(0, 0, 0), d = v3(0, 0, 1), idir = v3(0, 0, 0);    // the ray of the current level
         unsigned octinv = 0;
-        float    tmin = 0.f, tmax_w = 0.f, wlen = 1.f;
+        float    tmin = 0.f, tmin_w = 0.f, tmax_w = 0.f;
         uint32_t node_off = 0, tri_off = 0, cur = 0;
         Hit      loc { 0.f, 0.f, 0.f, INVALID_PRIM };     // best inside the current instance
         Hit      best { 0.f, 0.f, 0.f, INVALID_PRIM };    // best overall: t (object space if RENORM), u, v, flat prim
@@ -650,17 +663,6 @@ namespace crb
         uint32_t best_k = 0;
         uint2    group = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
         uint32_t local_next = 0, local_end = 0;
-
-        auto set_ray = [&](V3 ro, V3 rd) {
-            o = ro, d = rd;
-            idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-            octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
-        };
-        // TLAS traversal runs on the world ray with a unit direction (t = world distance) when RENORM, else on the ray as given
-        auto enter_tlas_ray = [&] {
-            set_ray(wo, RENORM ? wd * __frcp_rn(wlen) : wd);
-            node_off = 0, tri_off = 0, in_blas = false;
-        };
 
         for (;;)
         {
@@ -686,10 +688,9 @@ namespace crb
                 local_next += need < avail ? need : avail;
                 if (!active && rank < avail)
                 {
-                    source(base + rank, item, wo, wd, tmin, tmax_w);
+                    source(base + rank, item, wo, wd, tmin_w, tmax_w);
                     best     = Hit { tmax_w, 0.0f, 0.0f, INVALID_PRIM };
                     best_key = tmax_w, best_k = MARK;
-                    wlen     = RENORM ? __fsqrt_rn(dot(wd, wd)) : 1.0f;
                     if (sc.tlas.n_nodes == 0 || sc.n_inst == 0)
                     {
                         best.t   = __int_as_float(0x7f800000);
@@ -697,7 +698,13 @@ namespace crb
                     }
                     else
                     {
-                        enter_tlas_ray();
+                        // TLAS traversal runs on the world ray, with a unit direction (t = world distance) when RENORM
+                        td     = RENORM ? normalize(wd) : wd;
+                        tidir  = v3(safe_rcp(td.x), safe_rcp(td.y), safe_rcp(td.z));
+                        toct   = 7u ^ ((td.x < 0.0f ? 1u : 0u) | (td.y < 0.0f ? 2u : 0u) | (td.z < 0.0f ? 4u : 0u));
+                        o = wo, d = td, idir = tidir, octinv = toct;
+                        tmin   = RENORM ? 0.0f : tmin_w;
+                        node_off = 0, tri_off = 0, in_blas = false;
                         group  = make_uint2(0u, 0x80000000u);
                         tgroup = make_uint2(0u, 0u);
                         sp     = 0;
@@ -711,7 +718,8 @@ namespace crb
             for (int it = 0; it < STEPS; it++)
             {
                 // ---- node phase (TLAS or BLAS nodes: same layout)
-                if (active && tgroup.y == 0u && (group.y & 0xff000000u) != 0u)
+                const bool do_node = active && tgroup.y == 0u && (group.y & 0xff000000u) != 0u;
+                if (do_node)
                 {
                     const int bit = 31 - __clz(int(group.y & 0xff000000u));
                     group.y &= ~(1u << bit);
@@ -724,68 +732,89 @@ namespace crb
                     // far limit of the slab test: inside an instance the local best; in the TLAS the best so far (a world
                     // distance when RENORM, the ray parameter otherwise), loosened so that candidates within rounding are kept
                     const float    lim = in_blas ? loc.t : (RENORM ? best_key * 1.00001f : best_key);
-                    const unsigned h   = node_test(n0, n1, n2, n3, n4, o, idir, octinv, in_blas ? tmin : (RENORM ? 0.0f : tmin), lim);
+                    const unsigned h   = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, lim);
                     group              = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
                     tgroup             = make_uint2(n1.y, h & 0x00ffffffu);
                 }
-                // ---- leaf phase: one BLAS triangle, or one instance of a TLAS leaf
-                const bool pending = active && tgroup.y != 0u;
+                // ---- triangle phase: one BLAS triangle per lane that has some waiting
+                const bool pending = active && in_blas && tgroup.y != 0u;
                 if (__ballot_sync(FULL, pending) != 0u)
                 {
                     if (pending)
                     {
                         const int i = __ffs(int(tgroup.y)) - 1;
                         tgroup.y &= tgroup.y - 1;
-                        if (in_blas)
+                        const float4 *tp = sc.tris + (size_t(tri_off) + tgroup.x + unsigned(i)) * 3;
+                        const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
+                        if (COUNT) ctr->tris++;
+                        float t, u, v;
+                        if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, loc.t, t, u, v))
                         {
-                            const float4 *tp = sc.tris + (size_t(tri_off) + tgroup.x + unsigned(i)) * 3;
-                            const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
-                            if (COUNT) ctr->tris++;
-                            float t, u, v;
-                            if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, loc.t, t, u, v))
+                            const unsigned prim = __float_as_uint(a.w);
+                            if (t < loc.t || prim < loc.prim) loc = Hit { t, u, v, prim };
+                            if (any && !(tmax_w < __int_as_float(0x7f800000)))
                             {
-                                const unsigned prim = __float_as_uint(a.w);
-                                if (t < loc.t || prim < loc.prim) loc = Hit { t, u, v, prim };
-                                if (any && !(tmax_w < __int_as_float(0x7f800000)))
-                                {
-                                    // an unbounded shadow ray: any triangle of any instance ends the query
-                                    best = Hit { t, u, v, sc.inst[cur].flat_start + prim };
-                                    group.y = 0u, tgroup.y = 0u, sp = 0;
-                                    in_blas = false;
-                                }
+                                // an unbounded shadow ray: any triangle of any instance ends the query
+                                best = Hit { t, u, v, sc.inst[cur].flat_start + prim };
+                                group.y = 0u, tgroup.y = 0u, sp = 0;
+                                in_blas = false;
                             }
                         }
-                        else
+                    }
+                }
+                // ---- entry phase: lanes standing on a TLAS leaf take ONE of its instances into object space. The entry is long
+                // (two matrix products, a normalisation, three reciprocals) and rare per lane, so it runs when CRB_ENTRY_MIN
+                // lanes wait for it or nothing else in the warp can progress.
+                const bool     want  = active && !in_blas && tgroup.y != 0u;
+                const unsigned wantm = __ballot_sync(FULL, want);
+                if (wantm != 0u)
+                {
+                    // someone else can still do a node or a triangle next iteration?
+                    const unsigned busy = __ballot_sync(FULL, active && !want && (tgroup.y != 0u || (group.y & 0xff000000u) != 0u || sp > 0));
+                    if (__popc(wantm) >= CRB_ENTRY_MIN || busy == 0u)
+                    {
+                        if (want)
                         {
-                            // instance entry: the proxy triangle's id is the instance index
-                            const uint32_t  k  = __float_as_uint(__ldg(sc.tlas.tris + (size_t(tgroup.x) + unsigned(i)) * 3).w);
-                            const Instance &I  = sc.inst[k];
-                            const float     lim = RENORM ? best_key * 1.00001f : best_key;
-                            if (ray_box(o, idir, I.lo, I.hi, RENORM ? 0.0f : tmin, lim))
+                            const int i = __ffs(int(tgroup.y)) - 1;
+                            tgroup.y &= tgroup.y - 1;
+                            // the proxy triangle's id is the instance index; the record is nine 16-byte loads
+                            const uint32_t k  = __float_as_uint(__ldg(sc.tlas.tris + (size_t(tgroup.x) + unsigned(i)) * 3).w);
+                            const float4  *ip = reinterpret_cast<const float4 *>(sc.inst + k);
+                            const float4   i6 = __ldg(ip + 6), i7 = __ldg(ip + 7);
+                            const float    lo[3] = { i6.x, i6.y, i6.z }, hi[3] = { i7.x, i7.y, i7.z };
+                            const float    lim = RENORM ? best_key * 1.00001f : best_key;
+                            if (ray_box(o, idir, lo, hi, tmin, lim))
                             {
+                                const float4 v0 = __ldg(ip), v1 = __ldg(ip + 1), v2 = __ldg(ip + 2);
+                                const uint4  i8 = __ldg(reinterpret_cast<const uint4 *>(ip + 8));
+                                const float  inv[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
                                 if (group.y & 0xff000000u) stack[sp++] = group;
                                 if (tgroup.y) stack[sp++] = tgroup;    // the other instances of this TLAS leaf (high bits clear)
                                 stack[sp++] = make_uint2(MARK, 0u);
                                 cur = k;
                                 // model.cpp:107-112: inv * vec4(origin, 1), normalize(inv * vec4(direction, 0))
-                                const V3 oo = xf34(I.inv, wo, 1.0f);
-                                V3       dd = xf34(I.inv, wd, 0.0f);
-                                if (RENORM) dd = normalize(dd);
-                                set_ray(oo, dd);
-                                const Blas bl = sc.blas[I.blas];
-                                node_off = bl.node_base, tri_off = bl.tri_base, in_blas = true;
+                                o = xf34(inv, wo, 1.0f);
+                                d = xf34(inv, wd, 0.0f);
+                                if (RENORM) d = normalize(d);
+                                idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+                                octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+                                node_off = i8.x, tri_off = i8.y, in_blas = true;
                                 float bound = best_key;
                                 if (RENORM)
                                 {
-                                    // world distance per unit of object-space t along this ray = |fwd * d'|: a hit beyond
-                                    // best / that (loosened) cannot win the exact comparison made when the instance is left
-                                    const V3    wdir = xf34(I.fwd, dd, 0.0f);
-                                    const float c    = __fsqrt_rn(dot(wdir, wdir));
-                                    bound            = best_key < __int_as_float(0x7f800000) ? (best_key / c) * 1.0001f : best_key;
-                                    tmin             = 0.00001f;    // model.cpp:21
+                                    tmin = 0.00001f;    // model.cpp:21
+                                    if (best_key < __int_as_float(0x7f800000))
+                                    {
+                                        // world distance per unit of object-space t along this ray = |fwd * d'|: a hit beyond
+                                        // best / that (loosened) cannot win the exact comparison made when the instance is left
+                                        const float4 f0 = __ldg(ip + 3), f1 = __ldg(ip + 4), f2 = __ldg(ip + 5);
+                                        const float  fwd[12] = { f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w };
+                                        const V3     wdir = xf34(fwd, d, 0.0f);
+                                        bound             = (best_key / __fsqrt_rn(dot(wdir, wdir))) * 1.0001f;
+                                    }
                                 }
                                 loc    = Hit { bound, 0.0f, 0.0f, INVALID_PRIM };
-                                group  = make_uint2(0u, bl.n_nodes ? 0x80000000u : 0u);
+                                group  = make_uint2(0u, i8.z ? 0x80000000u : 0u);
                                 tgroup = make_uint2(0u, 0u);
                             }
                         }
@@ -806,22 +835,25 @@ namespace crb
                         // leave the instance: model.cpp:116-123 (map the point back, re-measure, keep the nearest)
                         if (loc.prim != INVALID_PRIM)
                         {
-                            float key = loc.t;
+                            const float4 *ip = reinterpret_cast<const float4 *>(sc.inst + cur);
+                            float         key = loc.t;
                             if (RENORM)
                             {
-                                const V3 p  = xf34(sc.inst[cur].fwd, o + d * loc.t, 1.0f);
-                                key         = length(p - wo);    // glm::distance(point, ray.origin)
+                                const float4 f0 = __ldg(ip + 3), f1 = __ldg(ip + 4), f2 = __ldg(ip + 5);
+                                const float  fwd[12] = { f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w };
+                                key                  = length(xf34(fwd, o + d * loc.t, 1.0f) - wo);    // glm::distance(point, ray.origin)
                             }
                             if ((key < best_key || (key == best_key && cur < best_k)) && key <= tmax_w)
                             {
-                                best     = Hit { loc.t, loc.u, loc.v, sc.inst[cur].flat_start + loc.prim };
+                                best     = Hit { loc.t, loc.u, loc.v, __float_as_uint(__ldg(ip + 7).w) + loc.prim };
                                 best_key = key, best_k = cur;
                                 if (any) sp = 0;    // a bounded shadow ray is blocked: done
                             }
                             loc.prim = INVALID_PRIM;
                         }
-                        if (RENORM) tmin = 0.0f;
-                        enter_tlas_ray();
+                        o = wo, d = td, idir = tidir, octinv = toct;
+                        tmin     = RENORM ? 0.0f : tmin_w;
+                        node_off = 0, tri_off = 0, in_blas = false;
                         continue;
                     }
                     if ((e.y & 0xff000000u) == 0u)

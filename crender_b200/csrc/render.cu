@@ -428,9 +428,14 @@ namespace crb
                             ms             = v3(c.x, c.y, c.z);
                         }
                         if (aov) rp.albedo[flipped_index(rp, x, y)] = make_float4(ms.x, ms.y, ms.z, 1.f);
-                        const float4 r4 = ps.rad[slot];
-                        const V3     r  = v3(r4.x, r4.y, r4.z) + thr * ms;
-                        ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                        if (ms.x != 0.f || ms.y != 0.f || ms.z != 0.f)
+                        {
+                            // (adding thr * 0 = +0 changes no bit of the non-negative sum: the 32-byte read-modify-write of
+                            // the radiance record is skipped for a black sky)
+                            const float4 r4 = ps.rad[slot];
+                            const V3     r  = v3(r4.x, r4.y, r4.z) + thr * ms;
+                            ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                        }
                     }
                     else
                     {
@@ -492,9 +497,13 @@ namespace crb
                             }
                             // renderer.cpp:310-312
                             thr             = thr * albedo;
-                            const float4 r4 = ps.rad[slot];
-                            const V3     r  = v3(r4.x, r4.y, r4.z) + thr * mat.emission;
-                            ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                            if (mat.emission != 0.0f)
+                            {
+                                // (same: thr * 0 = +0; only emitters touch the radiance record)
+                                const float4 r4 = ps.rad[slot];
+                                const V3     r  = v3(r4.x, r4.y, r4.z) + thr * mat.emission;
+                                ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
+                            }
                             ps.thr[slot]    = make_float4(thr.x, thr.y, thr.z, 0.f);
                             ps.ray_o[slot]  = make_float4(no.x, no.y, no.z, 0.f);
                             ps.ray_d[slot]  = make_float4(nd.x, nd.y, nd.z, 0.f);
@@ -812,8 +821,11 @@ namespace crb
         }
 
         // ------------------------------------------------------------------ two-level variants of the two traversal kernels
+#ifndef CRB_TRACE2_OCC
+#define CRB_TRACE2_OCC 3    // resident CTAs per SM of the two-level traversal kernels (80 registers)
+#endif
         template<bool COUNT>
-        __global__ void __launch_bounds__(256, 3) k_trace2(DScene sc, PathState ps)
+        __global__ void __launch_bounds__(256, CRB_TRACE2_OCC) k_trace2(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_IN];
             TravCounters   tc;
@@ -835,7 +847,7 @@ namespace crb
         }
 
         template<bool COUNT>
-        __global__ void __launch_bounds__(256, 3) k_shadow2(DScene sc, PathState ps)
+        __global__ void __launch_bounds__(256, CRB_TRACE2_OCC) k_shadow2(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_SHADOW];
             TravCounters   tc;
@@ -1238,7 +1250,7 @@ namespace crb
 #ifdef CRB_EMU
         const unsigned pgrid = 1, pblock = 1, tgrid = 1, t2grid = 1, sgrid = 1, sblock = 1;
 #else
-        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC, t2grid = unsigned(n_sms) * 3,
+        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC, t2grid = unsigned(n_sms) * CRB_TRACE2_OCC,
                        sgrid = unsigned(n_sms) * (1024 / CRB_SHADE_BLOCK), sblock = CRB_SHADE_BLOCK;
         const Span span { take_event(), take_event() };
         CRB_CUDA_CHECK(cudaEventRecord(span.a, stream()));

@@ -401,6 +401,7 @@ namespace crb
                     I.lo[r] = wlo[r] - pad, I.hi[r] = whi[r] + pad;
                 }
                 I.blas = uint32_t(mi), I.flat_start = uint32_t(flat_off);
+                I.node_base = blas_table[mi].node_base, I.tri_base = blas_table[mi].tri_base, I.n_nodes = blas_table[mi].n_nodes;
                 inst.push_back(I);
                 proxy.insert(proxy.end(), { I.lo[0], I.lo[1], I.lo[2], I.hi[0], I.hi[1], I.hi[2], I.lo[0], I.hi[1], I.lo[2] });
                 FlatRange r {};

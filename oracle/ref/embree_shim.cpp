@@ -4,9 +4,36 @@
 
 #include <embree3/rtcore.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <vector>
+
+// rtcIntersect1 calls, per thread (summed by ref_shim_intersect_calls): the metric counts every traversal query,
+// the reference's own counter (_total_rays) only path segments
+namespace
+{
+    std::mutex                                 g_mu;
+    std::vector<std::atomic<unsigned long long> *> g_counters;
+    struct Counter
+    {
+        std::atomic<unsigned long long> n { 0 };
+        Counter()
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            g_counters.push_back(&n);
+        }
+    };
+    thread_local Counter *t_counter = nullptr;
+}    // namespace
+extern "C" unsigned long long ref_shim_intersect_calls()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    unsigned long long          s = 0;
+    for (auto *c : g_counters) s += c->load(std::memory_order_relaxed);
+    return s;
+}
 
 struct RTCDeviceTy
 {
@@ -56,6 +83,8 @@ void rtcCommitScene(RTCScene s)
 }
 void rtcIntersect1(RTCScene s, struct RTCIntersectContext *, struct RTCRayHit *rh)
 {
+    if (!t_counter) t_counter = new Counter();    // (leaked with the thread: a handful per process)
+    t_counter->n.store(t_counter->n.load(std::memory_order_relaxed) + 1, std::memory_order_relaxed);
     const float o[3] = { rh->ray.org_x, rh->ray.org_y, rh->ray.org_z }, d[3] = { rh->ray.dir_x, rh->ray.dir_y, rh->ray.dir_z };
     float       t, u, v;
     uint32_t    prim;

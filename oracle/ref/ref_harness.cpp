@@ -50,6 +50,8 @@
 #include <thread>
 #include <unistd.h>
 
+extern "C" unsigned long long ref_shim_intersect_calls();
+
 namespace
 {
     struct Reader
@@ -210,13 +212,16 @@ namespace
         });
 
         // wait for the target (the management thread then blocks on _start_cond_var, renderer.cpp:139-141)
-        const auto t0 = std::chrono::steady_clock::now();
+        const unsigned long long calls0 = ref_shim_intersect_calls();
+        const auto               t0     = std::chrono::steady_clock::now();
         while (renderer->current_sample_count() < spp)
         {
-            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
             if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(600)) return fprintf(stderr, "ref_render: timeout\n"), 4;
         }
+        const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        const unsigned long long calls = ref_shim_intersect_calls() - calls0;
         const auto stats = renderer->current_stats();
 
         FILE *o = fopen(out, "wb");
@@ -224,6 +229,8 @@ namespace
         put(o, uint64_t(passes_before) * 2ull * w0 * h0);    // randf() draws consumed before the scene was handed over
         put(o, uint64_t(stats.total_rays));
         put(o, uint64_t(renderer->current_sample_count()));
+        put(o, uint64_t(calls));    // rtcIntersect1 calls = (closest-hit + shadow queries) x (model, instance) pairs
+        put(o, seconds);            // wall time from the end of update() to the last pass (all `threads` workers)
         put(o, renderer->_raw_buffer.data(), size_t(w) * h * 3);
         put(o, renderer->current_progress()->data(), size_t(w) * h * 4);
         put(o, renderer->current_albedos()->data(), size_t(w) * h * 4);

@@ -68,13 +68,13 @@ def scene_bytes(desc, w, h, bounces, spp, threads=1) -> bytes:
     return b"".join(out)
 
 
-def render(desc, w, h, bounces, spp, binary=None, timeout=15, retries=8) -> dict:
+def render(desc, w, h, bounces, spp, binary=None, timeout=15, retries=8, threads=1) -> dict:
     """Runs the compiled reference on `desc` with a one-thread pool. Returns raw (h,w,3) sums, the four RGBA images,
     and draws_before (randf() draws of the empty-scene passes the renderer completed before the scene was handed over)."""
     binary = binary or build()
     with tempfile.TemporaryDirectory() as d:
         src, dst = os.path.join(d, "scene.bin"), os.path.join(d, "out.bin")
-        open(src, "wb").write(scene_bytes(desc, w, h, bounces, spp))
+        open(src, "wb").write(scene_bytes(desc, w, h, bounces, spp, threads))
         for attempt in range(retries):
             # (the reference's pause()/thread-pool hand-shakes wait on condition variables without predicates,
             # renderer.cpp:172-183, thread_pool.cpp:12-13,55-56: a lost wake-up hangs it — time out and retry)
@@ -87,9 +87,10 @@ def render(desc, w, h, bounces, spp, binary=None, timeout=15, retries=8) -> dict
         else:
             raise RuntimeError("ref_render did not finish")
         raw = open(dst, "rb").read()
-    draws_before, total_rays, samples = struct.unpack_from("<3Q", raw, 0)
-    off, n = 24, w * h
-    out = {"draws_before": draws_before, "total_rays": total_rays, "samples": samples}
+    draws_before, total_rays, samples, calls = struct.unpack_from("<4Q", raw, 0)
+    (seconds,) = struct.unpack_from("<d", raw, 32)
+    off, n = 40, w * h
+    out = {"draws_before": draws_before, "total_rays": total_rays, "samples": samples, "intersect_calls": calls, "seconds": seconds}
     out["raw"] = np.frombuffer(raw, np.float32, n * 3, off).reshape(h, w, 3).copy()
     off += n * 12
     for k in ("progress", "albedo", "normal", "depth"):
