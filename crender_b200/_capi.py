@@ -82,6 +82,9 @@ class Stats(C.Structure):
         ("shadow_queries", C.c_uint64),
         ("kernel_ms", C.c_double * 8),
         ("kernel_count", C.c_uint64 * 8),
+        ("running_time", C.c_double),
+        ("rays_per_second", C.c_double),
+        ("samples_per_second", C.c_double),
     ]
 
 
@@ -133,6 +136,8 @@ SIGNATURES = {
     "crb_comm_unique_id": (C.c_int, [_P]),
     "crb_render_create_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "crb_render_set_sample_table": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32]),
+    "crb_render_set_target_spp": (C.c_int, [_P, C.c_uint64]),
+    "crb_render_run": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint64)]),
     "crb_render_flush": (C.c_int, [_P]),
     "crb_render_join_flush": (C.c_int, [_P]),
     "crb_render_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -300,11 +300,16 @@ class renderer:
 
     # ---- control (renderer.cpp:154-218)
     def start(self) -> bool:
-        """Clears the accumulation and, if a target spp is set, renders up to it."""
+        """Clears the accumulation and, if a target spp is set, renders up to it (the library's own target loop:
+        crb_render_set_target_spp + crb_render_run, renderer.cpp:116-144)."""
         _capi.check(self._lib, self._lib.crb_render_reset(self._h))
         self._next_sample = 0
         if self._spp_target:
-            self.render(self._spp_target)
+            total = C.c_uint64(0)
+            _capi.check(self._lib, self._lib.crb_render_set_target_spp(self._h, self._spp_target))
+            _capi.check(self._lib, self._lib.crb_render_run(self._h, 16, C.byref(total)))
+            _capi.check(self._lib, self._lib.crb_render_sync(self._h))
+            self._next_sample = int(total.value)
         return True
 
     def pause(self) -> bool:

@@ -9,6 +9,7 @@
 #include "render.cuh"
 #include "scene.cuh"
 
+#include <algorithm>
 #include <memory>
 #include <new>
 #include <string>
@@ -23,6 +24,7 @@ struct crb_render
     std::unique_ptr<crb::Render>      r;
     std::unique_ptr<crb::MultiRender> m;
     crb::Scene                       *scene = nullptr;
+    uint64_t                          target_spp = 0, submitted = 0;    // renderer::_spp_target and the passes handed to the device so far
     int device() const { return scene->device; }
 };
 
@@ -352,13 +354,17 @@ int crb_render_destroy(crb_render *r)
 }
 int crb_render_reset(crb_render *r)
 {
-    return on_render(r, [&](crb_render &h) { h.m ? h.m->reset() : h.r->reset(); });
+    return on_render(r, [&](crb_render &h) {
+        h.m ? h.m->reset() : h.r->reset();
+        h.submitted = 0;
+    });
 }
 int crb_render_set_resolution(crb_render *r, uint32_t w, uint32_t hh)
 {
     return on_render(r, [&](crb_render &h) {
         if (!w || !hh) throw crb::Error(crb::ERR_INVALID_ARG, "render target must be non-empty");
         h.m ? h.m->set_resolution(w, hh) : h.r->set_resolution(w, hh);
+        h.submitted = 0;
     });
 }
 int crb_render_set_max_bounces(crb_render *r, uint32_t b)
@@ -390,7 +396,32 @@ int crb_render_set_bands(crb_render *r, uint32_t band_rows, uint32_t first, uint
 }
 int crb_render_samples(crb_render *r, uint32_t first, uint32_t n)
 {
-    return on_render(r, [&](crb_render &h) { h.m ? h.m->render_samples(first, n) : h.r->render_samples(first, n); });
+    return on_render(r, [&](crb_render &h) {
+        h.m ? h.m->render_samples(first, n) : h.r->render_samples(first, n);
+        h.submitted = std::max<uint64_t>(h.submitted, uint64_t(first) + n);
+    });
+}
+int crb_render_set_target_spp(crb_render *r, uint64_t target)
+{
+    return on_render(r, [&](crb_render &h) { h.target_spp = target; });
+}
+int crb_render_run(crb_render *r, uint32_t passes_per_call, uint64_t *total)
+{
+    return on_render(r, [&](crb_render &h) {
+        if (passes_per_call == 0) passes_per_call = 1;
+        do
+        {
+            uint64_t n = passes_per_call;
+            if (h.target_spp)
+            {
+                if (h.submitted >= h.target_spp) break;
+                n = std::min<uint64_t>(n, h.target_spp - h.submitted);
+            }
+            h.m ? h.m->render_samples(uint32_t(h.submitted), uint32_t(n)) : h.r->render_samples(uint32_t(h.submitted), uint32_t(n));
+            h.submitted += n;
+        } while (h.target_spp);
+        if (total) *total = h.submitted;
+    });
 }
 int crb_render_flush(crb_render *r)
 {
@@ -432,6 +463,9 @@ int crb_render_stats(crb_render *r, crb_stats *out)
     return on_render(r, [&](crb_render &h) {
         need(out, "out");
         h.m ? h.m->stats(*out) : h.r->stats(*out);
+        out->running_time       = out->device_ms * 1e-3;
+        out->rays_per_second    = out->running_time > 0 ? double(out->ref_rays) / out->running_time : 0.0;
+        out->samples_per_second = out->running_time > 0 ? double(out->passes) / out->running_time : 0.0;
     });
 }
 int crb_render_restore(crb_render *r, const float *raw, uint32_t passes)
@@ -439,6 +473,7 @@ int crb_render_restore(crb_render *r, const float *raw, uint32_t passes)
     return on_render(r, [&](crb_render &h) {
         need(raw, "raw_sum_rgba_host");
         h.m ? h.m->restore(raw, passes) : h.r->restore(raw, passes);
+        h.submitted = passes;
     });
 }
 int crb_render_accum_ptr(crb_render *r, void **p, uint64_t *n)

@@ -226,7 +226,15 @@ namespace crb
         {
             check(crb_render_reset(_h));
             _next = 0;
-            if (_spp_target) render(uint32_t(_spp_target));
+            if (_spp_target)
+            {
+                // the library's own target loop (renderer.cpp:116-144): passes up to the target, 16 per call
+                uint64_t total = 0;
+                check(crb_render_set_target_spp(_h, _spp_target));
+                check(crb_render_run(_h, 16, &total));
+                check(crb_render_sync(_h));
+                _next = uint32_t(total);
+            }
             return true;
         }
         bool pause()

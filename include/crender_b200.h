@@ -125,6 +125,13 @@ typedef struct crb_stats
      * every launch on the handle's stream. index: CRB_K_* */
     double   kernel_ms[8];
     uint64_t kernel_count[8];
+    /* cr::renderer::renderer_stats as the reference defines it (renderer.h:48-54, renderer.cpp:396-404), with the device
+     * time spent in render kernels since the last reset in place of the wall clock: running_time, rays_per_second =
+     * ref_rays / running_time (path segments; shadow rays are not counted by the reference), samples_per_second =
+     * passes / running_time (whole-frame PASSES per second, which is what the reference calls samples) */
+    double   running_time;
+    double   rays_per_second;
+    double   samples_per_second;
 } crb_stats;
 enum { CRB_K_RAYGEN = 0, CRB_K_TRACE = 1, CRB_K_SHADE = 2, CRB_K_SHADOW = 3, CRB_K_ADVANCE = 4, CRB_K_ACCUMULATE = 5 };
 
@@ -221,6 +228,13 @@ int crb_render_set_bands(crb_render *, uint32_t band_rows, uint32_t first, uint3
  * (management thread + _get_tasks + _sample_pixel, renderer.cpp:116-144,240-384); asynchronous */
 int crb_render_samples(crb_render *, uint32_t first_sample, uint32_t n);
 int crb_render_sync(crb_render *);
+/* The reference's management thread renders passes until _spp_target is reached (0 = for ever), one pass per loop
+ * iteration (renderer.cpp:116-144; set_target_spp :215-218). crb_render_set_target_spp stores the target;
+ * crb_render_run submits the passes still missing — from the current pass count up to the target, passes_per_call at a
+ * time (the library batches them into wavefronts) — and returns without waiting, like renderer::start(). With target 0
+ * it submits one call of passes_per_call passes; a host loop around it is the reference's "render for ever". */
+int crb_render_set_target_spp(crb_render *, uint64_t target);
+int crb_render_run(crb_render *, uint32_t passes_per_call, uint64_t *passes_submitted_total);
 enum { CRB_RAW_SUM = 0, CRB_PROGRESS = 1, CRB_ALBEDO = 2, CRB_NORMAL = 3, CRB_DEPTH = 4 };
 /* current_progress/normals/albedos/depths (renderer.cpp:220-238): w*h*4 floats, row-major, x/y
  * flipped exactly as the reference stores them. CRB_RAW_SUM = _raw_buffer as RGBA with A = the pixel's own pass

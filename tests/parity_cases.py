@@ -713,3 +713,27 @@ def check_instance_edits(oracle, lib_path):
     g.set_flatten_instances(False)
     g.commit()
     np.testing.assert_array_equal(g.cast_rays(rays)["t"], ho["t"])
+
+
+def check_target_spp(lib_path):
+    """renderer::set_target_spp + start (renderer.cpp:116-144,154-170,215-218): the library's own loop renders exactly the
+    missing passes up to the target, in calls of 16; the result is the same render as one call; the reference-style
+    statistics (passes per second, path segments per second) are filled."""
+    desc = scenes.mesh_scene(40, 20)
+    g = api.scene(lib_path=lib_path)
+    scenes.load(desc, g)
+    g.commit()
+    r = api.renderer(64, 40, 5, g, seed=2)
+    r.render(37)
+    want = r.raw_sum().copy()
+    r2 = api.renderer(64, 40, 5, g, seed=2)
+    r2.set_target_spp(37)
+    r2.start()
+    st = r2.current_stats()
+    assert st.passes == 37 and r2.current_sample_count() == 37
+    np.testing.assert_array_equal(r2.raw_sum(), want)
+    r2.start()  # restart: renders to the target again from sample 0
+    np.testing.assert_array_equal(r2.raw_sum(), want)
+    if st.device_ms > 0:
+        assert st.running_time > 0 and abs(st.samples_per_second - 37 / st.running_time) < 1e-6 * st.samples_per_second
+        assert abs(st.rays_per_second - st.ref_rays / st.running_time) < 1e-6 * st.rays_per_second

@@ -75,3 +75,7 @@ def test_multi_gpu_handle(emu_lib, n):
 
 def test_instance_edits(oracle, emu_lib):
     pc.check_instance_edits(oracle, emu_lib)
+
+
+def test_target_spp(emu_lib):
+    pc.check_target_spp(emu_lib)

@@ -257,6 +257,10 @@ def test_against_golden_fixtures(product_lib):
         assert common.relrmse(r.raw_sum()[..., :3], gold[f"{name}/ext_raw"][..., :3]) <= pc.IMG_RELRMSE, name
 
 
+def test_target_spp(product_lib):
+    pc.check_target_spp(product_lib)
+
+
 def test_checkpoint_resume(product_lib):
     pc.check_checkpoint_resume(product_lib)
 
