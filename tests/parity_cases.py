@@ -737,3 +737,46 @@ def check_target_spp(lib_path):
     if st.device_ms > 0:
         assert st.running_time > 0 and abs(st.samples_per_second - 37 / st.running_time) < 1e-6 * st.samples_per_second
         assert abs(st.rays_per_second - st.ref_rays / st.running_time) < 1e-6 * st.rays_per_second
+
+
+def check_two_level_edge_cases(oracle, lib_path):
+    """Instanced scenes at the edges: a model with an EMPTY instance list is invisible, a thousand instances of a small
+    model (a TLAS several levels deep), an instance list mixing the identity with other transforms, coincident instances
+    (ties go to the first in the reference's loop order), all against the oracle, bit for bit."""
+    box = scenes._box((0, 0, 0), (0.2, 0.2, 0.2), 15.0).astype(np.float32)
+    ground = scenes._quad((-30, -0.5, -30), (-30, -0.5, 30), (30, -0.5, 30), (30, -0.5, -30)).astype(np.float32)
+    rs = np.random.RandomState(3)
+
+    def build(instances):
+        desc = scenes.SceneDesc("edge", [scenes.MeshDesc(ground, np.zeros(2, np.uint32), [material()], name="ground"),
+                                         scenes.MeshDesc(box, np.zeros(12, np.uint32), [material()], instances=instances, name="box")],
+                                api.camera(position=(0.0, 3.0, -12.0), fov=60.0, rotation=(0.0, 12.0, 0.0)))
+        return desc
+
+    cases = {
+        "thousand": np.stack([scenes.compose(scenes.translation(rs.uniform(-20, 20), rs.uniform(0, 3), rs.uniform(-20, 20)), scenes.rotation_y(rs.uniform(0, 360))) for _ in range(1000)]),
+        "identity_mixed": np.stack([np.eye(4, dtype=np.float32), scenes.translation(1.0, 0.5, 0.0), np.eye(4, dtype=np.float32)]),  # instances 0 and 2 coincide
+        "none": np.zeros((0, 4, 4), np.float32),
+    }
+    for name, inst in cases.items():
+        desc = build(inst.astype(np.float32))
+        o = oracle.scene()
+        scenes.load(desc, o)
+        o.commit()
+        g = api.scene(lib_path=lib_path)
+        scenes.load(desc, g)
+        info = g.commit()
+        assert info.n_triangles == 2 + 12 * len(inst), name
+        rays = common.mixed_rays(desc, 6000, seed=23)
+        ho, hg = o.cast_rays(rays), g.cast_rays(rays)
+        for f in ("prim", "model", "inst", "t", "u", "v"):
+            np.testing.assert_array_equal(hg[f], ho[f], err_msg=f"{name} {f}")
+        if name == "none":
+            assert not np.any(hg["model"] == 1)
+        np.testing.assert_array_equal(g.occluded(rays).astype(bool), hg["prim"] != common.MISS)
+        w, h = 48, 30
+        rg = api.renderer(w, h, 4, g, seed=1)
+        rg.render(2)
+        ro = oracle.renderer(w, h, 4, o, seed=1)
+        ro.render(2)
+        assert common.relrmse(rg.raw_sum()[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE, name

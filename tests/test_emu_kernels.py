@@ -79,3 +79,7 @@ def test_instance_edits(oracle, emu_lib):
 
 def test_target_spp(emu_lib):
     pc.check_target_spp(emu_lib)
+
+
+def test_two_level_edge_cases(oracle, emu_lib):
+    pc.check_two_level_edge_cases(oracle, emu_lib)

@@ -212,6 +212,10 @@ def test_instance_edits(oracle, product_lib):
     pc.check_instance_edits(oracle, product_lib)
 
 
+def test_two_level_edge_cases(oracle, product_lib):
+    pc.check_two_level_edge_cases(oracle, product_lib)
+
+
 def test_against_golden_fixtures(product_lib):
     """The CUDA path against the committed fixtures (no oracle at run time for this test)."""
     import os
