@@ -6,16 +6,28 @@
 //
 //   node  = 80 bytes = five uint4 loads:
 //     n0: origin.xyz (f32) | ex,ey,ez (biased power-of-two exponents) , imask (bit s: slot s is an inner node)
-//     n1: child_base (index of first inner child) | tri_base (index of first leaf triangle) | meta[8]
+//     n1: child_base (index of first inner child, < 2^24) | tri_base (index of first leaf triangle) | meta[8]
 //     n2: qlo.x[8] | qlo.y[8]        8-bit child boxes on the grid origin + q * 2^(e-127)
 //     n3: qlo.z[8] | qhi.x[8]
 //     n4: qhi.y[8] | qhi.z[8]
-//     meta[s]: 0 = empty; inner: 0x20 | (24+s); leaf: (unary triangle count 1/3/7) << 5 | first-triangle offset (0..23)
+//     meta[s]: 0 = empty; inner: 0x80; leaf: unary triangle count 1/3/7
 //   tri   = 48 bytes = three float4 loads: (v0, flat prim id) (e1=v1-v0, 0) (e2=v2-v0, 0)
+//   A node's leaf triangles are stored from tri_base in NIBBLE ORDER of the slots (0,4,1,5,2,6,3,7): the node's
+//   leaf occupancy word occ = ((meta[4..7] << 4) | meta[0..3]) & 0x77777777 has one bit per triangle, and the
+//   triangle behind bit i is tri_base + popc(occ & ((1 << i) - 1)). Inner children are stored from child_base in
+//   slot order (rank = popc(imask & ((1 << slot) - 1))).
 //
 // Children are assigned to slots at build time so that slot ^ (7 ^ ray octant) orders them front to
-// back; a node's hit children are kept as one 8-byte stack entry (base index, hit bits), following the
+// back; a node's hit children are kept as one 8-byte stack entry (base index | imask, hit flags), following the
 // compressed-wide-BVH scheme of Ylitie, Karras & Laine (HPG 2017) as published; the code is original.
+//
+// Hit-word assembly (round 2, see node_visit): ncu/SASS showed the node test bound by the ALU pipe, the conversion
+// unit and the issue slots at once (136 ALU + 34 XU + 85 FMA of 263 instructions; ALU and FMA issue every other
+// cycle per scheduler, the conversion unit every eighth). The per-child `bits = count << index` assembly of round 1
+// (61 ALU instructions) is replaced by byte-parallel work on ALL children at once: the eight slab results become
+// eight sign bits (one FFMA each), six PRMTs with sign replication turn them into two words of 0x00/0xff bytes,
+// two LOP3 mask the meta bytes with them, two PRMTs with a per-ray selector put the bytes in front-to-back order
+// and four shift/mask pairs split them into the inner-flag word, the leaf-triangle word and the occupancy word.
 //
 // The triangle test is Moeller-Trumbore with a fixed operation sequence of single roundings (see
 // tri_test) so that t,u,v are bit-identical to the CPU oracle; ties in t go to the lowest flat
@@ -30,12 +42,6 @@
 #endif
 #ifndef CRB_EARLY_POP
 #define CRB_EARLY_POP 2    // 1: +0.7 %, 2 (predicated in-place loads): +4.3 % (profiles/r1g_sweeps.md section 6)
-#endif
-
-// Leaf phase of the persistent trace loop: 0 = every lane tests one of ITS OWN waiting triangles per iteration (r1); 1 = all
-// waiting triangles of the warp are redistributed over all 32 lanes and tested at once (see trace_persistent)
-#ifndef CRB_COOP_LEAF
-#define CRB_COOP_LEAF 0    // measured: 2891 vs 3277 Mrays/s on config 2 (profiles/r2_sweeps.md): the redistribution costs more than the idle lanes
 #endif
 
 namespace crb
@@ -140,10 +146,54 @@ namespace crb
 #endif
     }
 
-    // Intersects the ray with the 8 child boxes of one node. Returns the hit bits: bits 24..31 = inner
-    // children at their traversal priority, bits 0..23 = leaf triangles (relative to tri_base).
-    __device__ __forceinline__ unsigned node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, V3 o, V3 idir,
-                                                  unsigned octinv, float tmin, float tmax)
+    // PTX prmt.b32 in its default mode: result byte i = byte (sel nibble i & 7) of {b,a}; nibble bit 3 set = the byte's
+    // sign bit replicated over all 8 bits. (__byte_perm only exposes the 3-bit form.)
+    __device__ __forceinline__ unsigned crb_prmt(unsigned a, unsigned b, unsigned sel)
+    {
+#ifdef CRB_EMU
+        const unsigned long long src = ((unsigned long long) b << 32) | a;
+        unsigned                 r   = 0;
+        for (int i = 0; i < 4; i++)
+        {
+            const unsigned n    = (sel >> (4 * i)) & 0xfu;
+            unsigned       byte = unsigned(src >> (8 * (n & 7u))) & 0xffu;
+            if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+            r |= byte << (8 * i);
+        }
+        return r;
+#else
+        unsigned d;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+        return d;
+#endif
+    }
+
+    // bit pattern whose SIGN BIT says "slab test failed": tf * slack - tn, one FFMA (on the GPU an inf - inf gives the
+    // canonical positive NaN = hit, conservative; the harness mirrors that, x86 would produce a negative NaN)
+    __device__ __forceinline__ unsigned slab_miss_sign(float tn, float tf)
+    {
+        const float diff = fmaf(tf, BVH8_BOX_SLACK, -tn);
+#ifdef CRB_EMU
+        if (diff != diff) return 0u;
+#endif
+        return __float_as_uint(diff);
+    }
+
+    // per-ray octant word: octinv = 7 ^ octant replicated in four nibbles (the low nibble is octinv itself). The PRMT
+    // selectors that put a node's child bytes in front-to-back order are 0x7531 ^ oct4 and 0x6420 ^ oct4.
+    __device__ __forceinline__ unsigned make_oct4(V3 d)
+    {
+        return (7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u))) * 0x1111u;
+    }
+
+    // What a node visit leaves behind (see the header comment):
+    //   group  = (child_base | imask << 24, inner-hit flags: bit 4p+3 = the hit inner child of front-to-back priority p)
+    //   tgroup = (tri_base, hit leaf triangles: bits of occ)
+    //   occ    = the node's leaf occupancy word (all its leaf triangles, hit or not): triangle of bit i = tri_base +
+    //            popc(occ & ((1 << i) - 1))
+    // Intersects the ray with the 8 child boxes of one node.
+    __device__ __forceinline__ void node_visit(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, V3 o, V3 idir, unsigned oct4,
+                                               float tmin, float tmax, uint2 &group, uint2 &tgroup, unsigned &occ)
     {
         const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
         const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
@@ -151,16 +201,8 @@ namespace crb
         const float    ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
         const float    bx = (px - o.x) * idir.x, by = (py - o.y) * idir.y, bz = (pz - o.z) * idir.z;
         const bool     nx = idir.x < 0.0f, ny = idir.y < 0.0f, nz = idir.z < 0.0f;
-        // inner children sit at priority bit 24 + (slot ^ octinv): their meta byte already holds 24 + slot,
-        // so the ray octant is folded in with one XOR on four bytes at a time (inner <=> bits 3 and 4 of the
-        // byte are set; leaf offsets are < 24). NOTE: an earlier per-slot form `inner ? 24 + (slot ^ octinv)
-        // : meta & 31` was miscompiled by ptxas 12.9 (the loop-invariant arm was hoisted out of the STEPS loop
-        // into a register that the predicated other arm then overwrote); keep the index
-        // computation free of loop-invariant select arms.
-        const unsigned octinv4 = octinv * 0x01010101u;
-        unsigned       hits    = 0;
 #if CRB_NODE_PRMT_AXES
-        const unsigned one = 0x3f800000u ^ (n1.x >> 31);    // child_base < 2^31: always 1.0f, but not a literal (see byte_as_float)
+        const unsigned one = 0x3f800000u ^ (n1.x >> 31);    // child_base < 2^24: always 1.0f, but not a literal (see byte_as_float)
         // folded slab constants; the offset b - a*2^15 is rounded once (<= |a| * 2^-9, i.e. 1/512 of a grid cell),
         // so the entry side is loosened downwards and the exit side upwards by 1/256 of a cell
         const float Ax = ax * 32768.0f, Bnx = (bx - Ax) - fabsf(ax) * 0.00390625f, Bfx = (bx - Ax) + fabsf(ax) * 0.00390625f;
@@ -171,18 +213,16 @@ namespace crb
         const float Az = az * 32768.0f, Bnz = (bz - Az) - fabsf(az) * 0.00390625f, Bfz = (bz - Az) + fabsf(az) * 0.00390625f;
 #endif
 #endif
+        unsigned miss[2];    // per half: byte j = 0xff if child 4*half + j is missed
 #pragma unroll
         for (int half = 0; half < 2; half++)
         {
-            const unsigned meta4      = half ? n1.w : n1.z;
-            const unsigned is_inner4  = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const unsigned index4     = (meta4 ^ (octinv4 & ((is_inner4 >> 4) * 0xffu))) & 0x1f1f1f1fu;
-            const unsigned childbits4 = (meta4 >> 5) & 0x07070707u;
             const unsigned lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
             const unsigned hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
             const unsigned nearx = nx ? hix : lox, farx = nx ? lox : hix;
             const unsigned neary = ny ? hiy : loy, fary = ny ? loy : hiy;
             const unsigned nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+            unsigned       sgn[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
             {
@@ -204,15 +244,38 @@ namespace crb
 #else
                 const float t0z = fmaf(float(byte_of(nearz, j)), az, bz), t1z = fmaf(float(byte_of(farz, j)), az, bz);
 #endif
-                const float    tn  = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-                const float    tf  = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-                // branch-free: leaves contribute their unary triangle count at their triangle offset, inner
-                // children one bit at their priority; an empty slot has meta == 0 -> 0 bits
-                const unsigned bits = byte_of(childbits4, j) << byte_of(index4, j);
-                hits |= (tn <= tf * BVH8_BOX_SLACK) ? bits : 0u;
+                const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+                const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+                sgn[j]         = slab_miss_sign(tn, tf);    // hit <=> tn <= tf * BVH8_BOX_SLACK
             }
+            // four sign bits -> four bytes 0x00 / 0xff (PRMT sign replication of the top byte of each difference)
+            const unsigned m01 = crb_prmt(sgn[0], sgn[1], 0xfbfbu), m23 = crb_prmt(sgn[2], sgn[3], 0xfbfbu);
+            miss[half]         = crb_prmt(m01, m23, 0x5410u);
         }
-        return hits;
+        // hit children keep their meta byte (inner 0x80, leaf unary count, empty 0)
+        const unsigned hlo = n1.z & ~miss[0], hhi = n1.w & ~miss[1];
+        // front-to-back order: byte k of pa = the child of priority 2k+1, of pb = priority 2k (priority p <-> slot p ^ octinv)
+        const unsigned pa = crb_prmt(hlo, hhi, 0x7531u ^ oct4), pb = crb_prmt(hlo, hhi, 0x6420u ^ oct4);
+        group             = make_uint2(n1.x | (n0.w & 0xff000000u), (pa | (pb >> 4)) & 0x88888888u);
+        tgroup            = make_uint2(n1.y, ((hhi << 4) | hlo) & 0x77777777u);
+        occ               = ((n1.w << 4) | n1.z) & 0x77777777u;
+    }
+
+    // the front-most unvisited inner child of a node group: removes it from the group, returns its node index
+    __device__ __forceinline__ unsigned pop_inner(uint2 &group, unsigned oct4)
+    {
+        const int bit = 31 - __clz(int(group.y));
+        group.y &= ~(1u << bit);
+        const unsigned slot = (unsigned(bit >> 2) ^ oct4) & 7u;
+        return (group.x & 0x00ffffffu) + __popc((group.x >> 24) & ((1u << slot) - 1u));
+    }
+
+    // the next waiting leaf triangle of a node: removes its bit, returns its index in the triangle array
+    __device__ __forceinline__ unsigned pop_triangle(uint2 &tgroup, unsigned occ)
+    {
+        const int i = __ffs(int(tgroup.y)) - 1;
+        tgroup.y &= tgroup.y - 1;
+        return tgroup.x + __popc(occ & ((1u << i) - 1u));
     }
 
     // Closest hit (ANY=false) or any hit (ANY=true) along o + t*d, t in (tmin, tmax].
@@ -225,37 +288,30 @@ namespace crb
             best.t = __int_as_float(0x7f800000);
             return best;
         }
-        const V3       idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-        const unsigned oct    = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
-        const unsigned octinv = 7u ^ oct;
+        const V3       idir = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+        const unsigned oct4 = make_oct4(d);
 
         uint2 stack[BVH8_STACK];
         int   sp = 0;
-        // node group: x = base node index, y = hit bits (24..31) | imask (0..7). The root is entered as
-        // the single hit child of a pseudo group with base 0 and an empty imask (relative index 0).
-        uint2 group = make_uint2(0u, 0x80000000u);
+        // node group: x = base node index | imask << 24, y = hit flags of the inner children (bit 4p+3, priority p). The
+        // root is entered as the single hit child of a pseudo group with base 0 and an empty imask (rank 0).
+        uint2    group = make_uint2(0u, 0x80000000u), tgroup;
+        unsigned occ;
 
         for (;;)
         {
             // pop the front-most unvisited inner child of the current group
-            const int bit = 31 - __clz(int(group.y & 0xff000000u));
-            group.y &= ~(1u << bit);
-            if (group.y & 0xff000000u) stack[sp++] = group;
-            const unsigned slot       = unsigned(bit - 24) ^ octinv;
-            const unsigned node_index = group.x + __popc(group.y & 0xffu & ((1u << slot) - 1u));
+            const unsigned node_index = pop_inner(group, oct4);
+            if (group.y) stack[sp++] = group;
 
             const uint4 *np = bvh.nodes + size_t(node_index) * 5;
             const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) ctr->nodes++;
-            const unsigned h = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, best.t);
-            group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
-            uint2 tgroup     = make_uint2(n1.y, h & 0x00ffffffu);
+            node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, best.t, group, tgroup, occ);
 
             while (tgroup.y)
             {
-                const int i = __ffs(int(tgroup.y)) - 1;
-                tgroup.y &= tgroup.y - 1;
-                const float4 *tp = bvh.tris + size_t(tgroup.x + unsigned(i)) * 3;
+                const float4 *tp = bvh.tris + size_t(pop_triangle(tgroup, occ)) * 3;
                 const float4  a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 if (COUNT) ctr->tris++;
                 float t, u, v;
@@ -267,7 +323,7 @@ namespace crb
                 }
             }
 
-            if ((group.y & 0xff000000u) == 0)
+            if (group.y == 0u)
             {
                 if (sp == 0) break;
                 group = stack[--sp];
@@ -288,18 +344,10 @@ namespace crb
     // traversal state in registers. Lanes reconverge every STEPS node iterations, where finished rays are
     // handed to `sink` (which may itself use warp-aggregated queue pushes) and idle lanes are refilled.
     //
-    // Leaf phase (CRB_COOP_LEAF): a node visit leaves a lane with 0..24 triangles to test. Testing them one per lane per
-    // iteration (r1) kept ~11 of 32 lanes out of the node phase while they worked through their triangles, and ran the
-    // triangle test at ~8 active lanes (ncu r1j: 20-23 lanes per instruction overall). Now every iteration's waiting
-    // triangles of ALL lanes are written to a per-warp work list in shared memory (round k of the list = the k-th
-    // triangle of every lane that has one: positions from a ballot), and lane j tests work item j against the owner's
-    // ray (o, d, tmin in shared memory since the refill; the owner's current tfar by shuffle). Winners are merged per
-    // owner with a 64-bit shared-memory atomicMin on (t bits, prim) — t > 0, so the float order is the integer order and
-    // ties in t go to the lowest primitive id exactly as in the sequential loop (the accepted set {t <= tfar at the
-    // start} contains the sequential winner, and the lexicographic minimum of it IS the sequential winner). After the
-    // leaf phase no lane has triangles waiting, so every active lane takes part in every node phase. Visit order, hit
-    // records and traversal counters are bit-identical to the one-per-lane form (tests: check_instrumented_render_is_
-    // identical, the emu-vs-oracle exact comparisons, any-hit == closest-hit existence).
+    // Every iteration is a node phase (lanes without waiting triangles visit one node) followed by a leaf phase in
+    // lock step (every lane with waiting triangles tests ONE of them). A warp-cooperative leaf phase (all waiting
+    // triangles of the warp redistributed over the 32 lanes through shared memory) was built, kept bit-identical and
+    // measured 12 % slower (profiles/r2_sweeps.md section 1); it is no longer in the source.
     //
     //   source(idx, item, o, d, tmin, tmax)  loads work item idx (called by the lane that owns it)
     //   sink(valid, item, hit)               called by ALL lanes at a convergent point; valid lanes retire
@@ -311,21 +359,12 @@ namespace crb
     {
         const unsigned FULL = 0xffffffffu;
         const unsigned lane = crb_lane_id();
-#if CRB_COOP_LEAF
-        constexpr int TP_WARPS = 8;    // warps per CTA of every kernel that runs this loop (256 threads)
-        __shared__ float4             s_ray_o[TP_WARPS][CRB_WARP], s_ray_d[TP_WARPS][CRB_WARP];    // o.xyz,tmin | d.xyz
-        __shared__ uint2              s_item[TP_WARPS][CRB_WARP];                                  // triangle index, owner lane
-        __shared__ unsigned long long s_key[TP_WARPS][CRB_WARP];                                   // per owner: min (t bits << 32 | prim)
-        __shared__ float2             s_uv[TP_WARPS][CRB_WARP];                                    // per owner: the winner's barycentrics
-        const unsigned wib = (threadIdx.x / CRB_WARP) % TP_WARPS;
-        s_key[wib][lane]   = ~0ull;
-#endif
         uint2          stack[BVH8_STACK];
         int            sp = 0;
         bool           active = false, finished = false, exhausted = false;
         uint32_t       item = 0;
         V3             o = v3(0, 0, 0), d = v3(0, 0, 1), idir = v3(0, 0, 0);
-        unsigned       octinv = 0;
+        unsigned       oct4 = 0, occ = 0;
         float          tmin = 0.f;
         Hit            best { 0.f, 0.f, 0.f, INVALID_PRIM };
         uint2          group = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
@@ -369,10 +408,6 @@ namespace crb
                     {
                         float tmax;
                         source(idx, item, o, d, tmin, tmax);
-#if CRB_COOP_LEAF
-                        s_ray_o[wib][lane] = make_float4(o.x, o.y, o.z, tmin);
-                        s_ray_d[wib][lane] = make_float4(d.x, d.y, d.z, 0.0f);
-#endif
                         best = Hit { tmax, 0.0f, 0.0f, INVALID_PRIM };
                         if (bvh.n_nodes == 0)
                         {
@@ -382,7 +417,7 @@ namespace crb
                         else
                         {
                             idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-                            octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+                            oct4   = make_oct4(d);
                             group  = make_uint2(0u, 0x80000000u);
                             tgroup = make_uint2(0u, 0u);
                             sp     = 0;
@@ -399,18 +434,13 @@ namespace crb
                 // ---- node phase: lanes without pending triangles visit one node
                 if (active && tgroup.y == 0u)
                 {
-                    const int bit = 31 - __clz(int(group.y & 0xff000000u));
-                    group.y &= ~(1u << bit);
-                    if (group.y & 0xff000000u) stack[sp++] = group;
-                    const unsigned slot       = unsigned(bit - 24) ^ octinv;
-                    const unsigned node_index = group.x + __popc(group.y & 0xffu & ((1u << slot) - 1u));
+                    const unsigned node_index = pop_inner(group, oct4);
+                    if (group.y) stack[sp++] = group;
 
                     const uint4 *np = bvh.nodes + size_t(node_index) * 5;
                     const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                     if (COUNT) ctr->nodes++;
-                    const unsigned h = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, best.t);
-                    group            = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
-                    tgroup           = make_uint2(n1.y, h & 0x00ffffffu);
+                    node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, best.t, group, tgroup, occ);
                 }
 #if CRB_EARLY_POP
                 // ---- pop BEFORE the leaf phase: a lane whose node group has no inner child left will need the next
@@ -423,7 +453,7 @@ namespace crb
                     // predicated local loads straight into group's registers: written in C++ (or as one 64-bit
                     // load), ptxas loads into a temporary pair and moves it into `group` at once, i.e. waits for the
                     // load right here; two 32-bit loads have no register-pair constraint and need no move
-                    const bool pop = active && (group.y & 0xff000000u) == 0u && sp > 0;
+                    const bool pop = active && group.y == 0u && sp > 0;
                     sp -= pop ? 1 : 0;
                     const size_t a = __cvta_generic_to_local(&stack[sp]);
                     asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.local.u32 %0, [%3];\n @p ld.local.u32 %1, [%3+4];\n}"
@@ -432,85 +462,9 @@ namespace crb
                                  : "memory");
                 }
 #else
-                if (active && (group.y & 0xff000000u) == 0u && sp > 0) group = stack[--sp];
+                if (active && group.y == 0u && sp > 0) group = stack[--sp];
 #endif
 #endif
-#if CRB_COOP_LEAF
-                // ---- leaf phase, warp-cooperative: all waiting triangles of all lanes, redistributed over the lanes
-                if (__ballot_sync(FULL, active && tgroup.y != 0u) != 0u)
-                {
-                    const unsigned lt    = (1u << lane) - 1u;
-                    unsigned       total = 0;
-                    for (;;)
-                    {
-                        // round: one more triangle from every lane that still has one
-                        const bool     have = active && tgroup.y != 0u;
-                        const unsigned m    = __ballot_sync(FULL, have);
-                        const unsigned n    = unsigned(__popc(m));
-                        if (n == 0u || total + n > unsigned(CRB_WARP))
-                        {
-                            // ---- flush: lane j tests work item j
-                            __syncwarp();
-                            const bool     mine  = lane < total;
-                            const uint2    wi    = mine ? s_item[wib][lane] : make_uint2(0u, lane);
-                            const unsigned owner = wi.y;
-                            const float    tf    = __shfl_sync(FULL, best.t, int(owner));
-                            bool               hit = false;
-                            unsigned long long key = ~0ull;
-                            float              t = 0.f, u = 0.f, v = 0.f;
-                            if (mine)
-                            {
-                                const float4 *tp = bvh.tris + size_t(wi.x) * 3;
-                                const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
-                                const float4  ro = s_ray_o[wib][owner], rd = s_ray_d[wib][owner];
-                                if (COUNT) ctr->tris++;
-                                hit = tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), v3(ro.x, ro.y, ro.z), v3(rd.x, rd.y, rd.z), ro.w, tf, t, u, v);
-                                if (hit)
-                                {
-                                    key = ((unsigned long long) __float_as_uint(t) << 32) | (unsigned long long) __float_as_uint(a.w);
-                                    atomicMin(&s_key[wib][owner], key);
-                                }
-                            }
-                            __syncwarp();
-                            if (hit && s_key[wib][owner] == key) s_uv[wib][owner] = make_float2(u, v);
-                            __syncwarp();
-                            {
-                                // owners take their winner (same rule as the sequential loop: t < best.t, or equal t and lower id)
-                                const unsigned long long k = s_key[wib][lane];
-                                if (k != ~0ull)
-                                {
-                                    const float    kt = __uint_as_float(unsigned(k >> 32));
-                                    const unsigned kp = unsigned(k & 0xffffffffull);
-                                    if (kt < best.t || kp < best.prim)
-                                    {
-                                        const float2 uv = s_uv[wib][lane];
-                                        best            = Hit { kt, uv.x, uv.y, kp };
-                                    }
-                                    if (any)
-                                    {
-                                        // any hit ends the query: drop all remaining work, the advance step below retires the ray
-                                        group.y  = 0u;
-                                        tgroup.y = 0u;
-                                        sp       = 0;
-                                    }
-                                    s_key[wib][lane] = ~0ull;
-                                }
-                            }
-                            __syncwarp();
-                            total = 0;
-                            if (n == 0u) break;
-                            continue;    // re-ballot: an any-hit may have emptied lanes
-                        }
-                        if (have)
-                        {
-                            const int i = __ffs(int(tgroup.y)) - 1;
-                            tgroup.y &= tgroup.y - 1;
-                            s_item[wib][total + unsigned(__popc(m & lt))] = make_uint2(tgroup.x + unsigned(i), lane);
-                        }
-                        total += n;
-                    }
-                }
-#else
                 // ---- leaf phase in lock step: ONE triangle per lane that has triangles waiting (an inner
                 // per-lane triangle loop was 52 % of k_trace's instructions at 2.7 active lanes; waiting for
                 // more lanes to have triangles was measured and is slower, profiles/r1c_sweeps.md §6)
@@ -519,9 +473,7 @@ namespace crb
                 {
                     if (pending)
                     {
-                        const int i = __ffs(int(tgroup.y)) - 1;
-                        tgroup.y &= tgroup.y - 1;
-                        const float4 *tp = bvh.tris + size_t(tgroup.x + unsigned(i)) * 3;
+                        const float4 *tp = bvh.tris + size_t(pop_triangle(tgroup, occ)) * 3;
                         const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
                         if (COUNT) ctr->tris++;
                         float t, u, v;
@@ -540,9 +492,8 @@ namespace crb
                         }
                     }
                 }
-#endif
                 // ---- advance: nothing left in this node group -> pop, or retire the ray
-                if (active && tgroup.y == 0u && (group.y & 0xff000000u) == 0u)
+                if (active && tgroup.y == 0u && group.y == 0u)
                 {
 #if CRB_EARLY_POP
                     // the early pop found the stack empty (or an any-hit dropped everything): retire
@@ -621,7 +572,7 @@ namespace crb
         return tn <= tf * 1.00001f + 1e-30f || !(tn == tn) || !(tf == tf);    // NaN (origin on a face of a flat box): enter
     }
 
-    constexpr int BVH2_STACK = 80;    // TLAS levels + one marker per instance entry + BLAS levels
+    constexpr int BVH2_STACK = 80;    // TLAS levels + marker and pending-leaf entries of one instance entry + BLAS levels
 
     // Persistent two-level trace loop (same per-lane refill scheme as trace_persistent).
     //   RENORM = true : scene::cast_ray semantics (the renderer): per instance the direction is renormalised, the BLAS is
@@ -654,7 +605,7 @@ namespace crb
         V3       td = v3(0, 0, 1), tidir = v3(0, 0, 0);                  // the TLAS-level ray (unit direction when RENORM)
         unsigned toct = 0;
         V3       o = v3(0, 0, 0), d = v3(0, 0, 1), idir = v3(0, 0, 0);    // the ray of the current level
-        unsigned octinv = 0;
+        unsigned oct4 = 0, occ = 0;
         float    tmin = 0.f, tmin_w = 0.f, tmax_w = 0.f;
         uint32_t node_off = 0, tri_off = 0, cur = 0;
         Hit      loc { 0.f, 0.f, 0.f, INVALID_PRIM };     // best inside the current instance
@@ -701,8 +652,8 @@ namespace crb
                         // TLAS traversal runs on the world ray, with a unit direction (t = world distance) when RENORM
                         td     = RENORM ? normalize(wd) : wd;
                         tidir  = v3(safe_rcp(td.x), safe_rcp(td.y), safe_rcp(td.z));
-                        toct   = 7u ^ ((td.x < 0.0f ? 1u : 0u) | (td.y < 0.0f ? 2u : 0u) | (td.z < 0.0f ? 4u : 0u));
-                        o = wo, d = td, idir = tidir, octinv = toct;
+                        toct   = make_oct4(td);
+                        o = wo, d = td, idir = tidir, oct4 = toct;
                         tmin   = RENORM ? 0.0f : tmin_w;
                         node_off = 0, tri_off = 0, in_blas = false;
                         group  = make_uint2(0u, 0x80000000u);
@@ -718,23 +669,18 @@ namespace crb
             for (int it = 0; it < STEPS; it++)
             {
                 // ---- node phase (TLAS or BLAS nodes: same layout)
-                const bool do_node = active && tgroup.y == 0u && (group.y & 0xff000000u) != 0u;
+                const bool do_node = active && tgroup.y == 0u && group.y != 0u;
                 if (do_node)
                 {
-                    const int bit = 31 - __clz(int(group.y & 0xff000000u));
-                    group.y &= ~(1u << bit);
-                    if (group.y & 0xff000000u) stack[sp++] = group;
-                    const unsigned slot       = unsigned(bit - 24) ^ octinv;
-                    const unsigned node_index = group.x + __popc(group.y & 0xffu & ((1u << slot) - 1u));
+                    const unsigned node_index = pop_inner(group, oct4);
+                    if (group.y) stack[sp++] = group;
                     const uint4   *np = (in_blas ? sc.nodes + size_t(node_off) * 5 : sc.tlas.nodes) + size_t(node_index) * 5;
                     const uint4    n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                     if (COUNT) ctr->nodes++;
                     // far limit of the slab test: inside an instance the local best; in the TLAS the best so far (a world
                     // distance when RENORM, the ray parameter otherwise), loosened so that candidates within rounding are kept
                     const float    lim = in_blas ? loc.t : (RENORM ? best_key * 1.00001f : best_key);
-                    const unsigned h   = node_test(n0, n1, n2, n3, n4, o, idir, octinv, tmin, lim);
-                    group              = make_uint2(n1.x, (h & 0xff000000u) | (n0.w >> 24));
-                    tgroup             = make_uint2(n1.y, h & 0x00ffffffu);
+                    node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, lim, group, tgroup, occ);
                 }
                 // ---- triangle phase: one BLAS triangle per lane that has some waiting
                 const bool pending = active && in_blas && tgroup.y != 0u;
@@ -742,9 +688,7 @@ namespace crb
                 {
                     if (pending)
                     {
-                        const int i = __ffs(int(tgroup.y)) - 1;
-                        tgroup.y &= tgroup.y - 1;
-                        const float4 *tp = sc.tris + (size_t(tri_off) + tgroup.x + unsigned(i)) * 3;
+                        const float4 *tp = sc.tris + (size_t(tri_off) + pop_triangle(tgroup, occ)) * 3;
                         const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
                         if (COUNT) ctr->tris++;
                         float t, u, v;
@@ -770,15 +714,13 @@ namespace crb
                 if (wantm != 0u)
                 {
                     // someone else can still do a node or a triangle next iteration?
-                    const unsigned busy = __ballot_sync(FULL, active && !want && (tgroup.y != 0u || (group.y & 0xff000000u) != 0u || sp > 0));
+                    const unsigned busy = __ballot_sync(FULL, active && !want && (tgroup.y != 0u || group.y != 0u || sp > 0));
                     if (__popc(wantm) >= CRB_ENTRY_MIN || busy == 0u)
                     {
                         if (want)
                         {
-                            const int i = __ffs(int(tgroup.y)) - 1;
-                            tgroup.y &= tgroup.y - 1;
                             // the proxy triangle's id is the instance index; the record is nine 16-byte loads
-                            const uint32_t k  = __float_as_uint(__ldg(sc.tlas.tris + (size_t(tgroup.x) + unsigned(i)) * 3).w);
+                            const uint32_t k  = __float_as_uint(__ldg(sc.tlas.tris + size_t(pop_triangle(tgroup, occ)) * 3).w);
                             const float4  *ip = reinterpret_cast<const float4 *>(sc.inst + k);
                             const float4   i6 = __ldg(ip + 6), i7 = __ldg(ip + 7);
                             const float    lo[3] = { i6.x, i6.y, i6.z }, hi[3] = { i7.x, i7.y, i7.z };
@@ -788,8 +730,14 @@ namespace crb
                                 const float4 v0 = __ldg(ip), v1 = __ldg(ip + 1), v2 = __ldg(ip + 2);
                                 const uint4  i8 = __ldg(reinterpret_cast<const uint4 *>(ip + 8));
                                 const float  inv[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
-                                if (group.y & 0xff000000u) stack[sp++] = group;
-                                if (tgroup.y) stack[sp++] = tgroup;    // the other instances of this TLAS leaf (high bits clear)
+                                if (group.y) stack[sp++] = group;
+                                if (tgroup.y)
+                                {
+                                    // the other instances of this TLAS leaf: (occupancy word) below (triangle base, waiting bits);
+                                    // waiting bits lie in 0x77777777, inner-hit flags in 0x88888888: the entry kinds cannot be confused
+                                    stack[sp++] = make_uint2(occ, 0u);
+                                    stack[sp++] = tgroup;
+                                }
                                 stack[sp++] = make_uint2(MARK, 0u);
                                 cur = k;
                                 // model.cpp:107-112: inv * vec4(origin, 1), normalize(inv * vec4(direction, 0))
@@ -797,7 +745,7 @@ namespace crb
                                 d = xf34(inv, wd, 0.0f);
                                 if (RENORM) d = normalize(d);
                                 idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-                                octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+                                oct4   = make_oct4(d);
                                 node_off = i8.x, tri_off = i8.y, in_blas = true;
                                 float bound = best_key;
                                 if (RENORM)
@@ -821,7 +769,7 @@ namespace crb
                     }
                 }
                 // ---- advance: pop node groups / pending instances / instance markers, or retire
-                while (active && tgroup.y == 0u && (group.y & 0xff000000u) == 0u)
+                while (active && tgroup.y == 0u && group.y == 0u)
                 {
                     if (sp == 0)
                     {
@@ -851,13 +799,16 @@ namespace crb
                             }
                             loc.prim = INVALID_PRIM;
                         }
-                        o = wo, d = td, idir = tidir, octinv = toct;
+                        o = wo, d = td, idir = tidir, oct4 = toct;
                         tmin     = RENORM ? 0.0f : tmin_w;
                         node_off = 0, tri_off = 0, in_blas = false;
                         continue;
                     }
-                    if ((e.y & 0xff000000u) == 0u)
-                        tgroup = e;    // pending instances of a TLAS leaf
+                    if ((e.y & 0x88888888u) == 0u)
+                    {
+                        tgroup = e;    // pending instances of a TLAS leaf, their occupancy word below
+                        occ    = stack[--sp].x;
+                    }
                     else
                         group = e;
                 }

@@ -430,14 +430,29 @@ namespace crb
 
             unsigned meta[8], qlo[3][8], qhi[3][8];
             unsigned imask = 0;
-            int      inner_i = 0, tri_off = 0;
+            int      inner_i = 0;
             float    leaf_area_tris = 0.f;
+            // leaf triangles are stored in NIBBLE order of the slots (0,4,1,5,2,6,3,7): the order of the bits of the
+            // traversal's occupancy word ((meta[4..7] << 4) | meta[0..3]) & 0x77777777 (bvh8.cuh)
+            int tri_off_of[8];
+            {
+                int off = 0;
+                for (int nb = 0; nb < 8; nb++)
+                {
+                    const int s = ((nb & 1) << 2) | (nb >> 1), j = child_in_slot[s];
+                    tri_off_of[s] = off;
+                    if (j < 0) continue;
+                    const int cnt = ref_count(c.t, ch[j]);
+                    if (cnt <= BVH8_LEAF_TRIS) off += cnt;
+                }
+            }
             for (int s = 0; s < 8; s++)
             {
                 meta[s] = 0;
                 for (int a = 0; a < 3; a++) qlo[a][s] = 255u, qhi[a][s] = 0u;
                 const int j = child_in_slot[s];
                 if (j < 0) continue;
+                const int tri_off = tri_off_of[s];
                 const float lo3[3] = { clo[j].x, clo[j].y, clo[j].z }, hi3[3] = { chi[j].x, chi[j].y, chi[j].z };
                 for (int a = 0; a < 3; a++)
                 {
@@ -454,7 +469,7 @@ namespace crb
                 const int cnt = ref_count(c.t, ch[j]);
                 if (cnt <= BVH8_LEAF_TRIS)
                 {
-                    meta[s]         = (((1u << cnt) - 1u) << 5) | unsigned(tri_off);
+                    meta[s]         = (1u << cnt) - 1u;
                     int leaves[BVH8_LEAF_TRIS];
                     ref_leaves(c.t, ch[j], leaves);
                     for (int q = 0; q < cnt; q++)
@@ -466,12 +481,11 @@ namespace crb
                         dst[1]              = make_float4(__fsub_rn(v[3], v[0]), __fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), 0.f);
                         dst[2]              = make_float4(__fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]), __fsub_rn(v[8], v[2]), 0.f);
                     }
-                    tri_off += cnt;
                     leaf_area_tris += box_area(clo[j], chi[j]) * float(cnt);
                 }
                 else
                 {
-                    meta[s] = 0x20u | unsigned(24 + s);
+                    meta[s] = 0x80u;
                     imask |= 1u << s;
                     out[out_base + uint32_t(inner_i)] = make_uint2(unsigned(ch[j]), child_base + uint32_t(inner_i));
                     inner_i++;
@@ -680,9 +694,36 @@ namespace crb
         stats.n_nodes = fin[0], stats.n_tris = fin[1], stats.max_depth = depth;
         memcpy(&stats.sah_cost, &fin[4], 4);
         if (stats.n_tris != n) throw Error(ERR_GENERIC, "internal: triangle count mismatch after collapse");
+        if (stats.n_nodes > 0x00ffffffu) throw Error(ERR_BUILD_INDEX, "too many BVH nodes for the 24-bit child index of the traversal's stack entry");
         if (depth > uint32_t(BVH8_STACK)) throw Error(ERR_BVH_DEPTH, "BVH depth " + std::to_string(depth) + " exceeds the traversal stack");
 #ifdef CRB_EMU
         stats.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (getenv("CRB_BUILD_STATS"))
+        {
+            // kernel-logic harness only: occupancy of the 8 child slots (tools/tree_quality.py)
+            unsigned long long hc[9] = {}, hi_[9] = {}, hl[9] = {}, halves[4] = {};
+            for (uint32_t i = 0; i < stats.n_nodes; i++)
+            {
+                const uint4 n1 = nodes.p[size_t(i) * 5 + 1];
+                int nc = 0, nin = 0, lo4 = 0, hi4 = 0;
+                for (int s = 0; s < 8; s++)
+                {
+                    const unsigned m = ((s < 4 ? n1.z : n1.w) >> (8 * (s & 3))) & 0xffu;
+                    if (!m) continue;
+                    nc++, (s < 4 ? lo4 : hi4)++;
+                    if (m == 0x80u) nin++;
+                }
+                hc[nc]++, hi_[nin]++, hl[nc - nin]++;
+                halves[(lo4 ? 1 : 0) | (hi4 ? 2 : 0)]++;
+            }
+            fprintf(stderr, "children/node:");
+            for (int k = 0; k <= 8; k++) fprintf(stderr, " %d:%.3f", k, double(hc[k]) / stats.n_nodes);
+            fprintf(stderr, "\ninner/node:");
+            for (int k = 0; k <= 8; k++) fprintf(stderr, " %d:%.3f", k, double(hi_[k]) / stats.n_nodes);
+            fprintf(stderr, "\nleaves/node:");
+            for (int k = 0; k <= 8; k++) fprintf(stderr, " %d:%.3f", k, double(hl[k]) / stats.n_nodes);
+            fprintf(stderr, "\n");
+        }
 #else
         CRB_CUDA_CHECK(cudaEventRecord(ev1, stream));
         CRB_CUDA_CHECK(cudaEventSynchronize(ev1));
