@@ -591,6 +591,12 @@ namespace crb
 #ifndef CRB_ENTRY_MIN
 #define CRB_ENTRY_MIN 6
 #endif
+    // The query as given and the TLAS-level ray (13 values per lane) are only needed when a lane enters or leaves an
+    // instance: kept in shared memory instead of registers (CTAs of 256 threads: 16 KB), which is what lets the loop fit
+    // the register budget of one more resident CTA per SM.
+#ifndef CRB_2L_SMEM
+#define CRB_2L_SMEM 1
+#endif
     template<bool COUNT, int STEPS, bool RENORM, typename Source, typename Sink>
     __device__ __forceinline__ void trace_persistent_2l(const Bvh2 &sc, uint32_t *cursor, uint32_t n, bool any, Source source, Sink sink, TravCounters *ctr)
     {
@@ -601,12 +607,16 @@ namespace crb
         int      sp = 0;
         bool     active = false, finished = false, exhausted = false, in_blas = false;
         uint32_t item = 0;
-        V3       wo = v3(0, 0, 0), wd = v3(0, 0, 1);                     // the query as given (world)
-        V3       td = v3(0, 0, 1), tidir = v3(0, 0, 0);                  // the TLAS-level ray (unit direction when RENORM)
-        unsigned toct = 0;
+#if CRB_2L_SMEM && !defined(CRB_EMU)
+        __shared__ float4 s_wo[256], s_wd[256], s_td[256], s_ti[256];    // (wo, tmin_w) (wd, tmax_w) (td, toct) (tidir, -)
+        float4 &r_wo = s_wo[threadIdx.x], &r_wd = s_wd[threadIdx.x], &r_td = s_td[threadIdx.x], &r_ti = s_ti[threadIdx.x];
+#else
+        float4 r_wo = make_float4(0, 0, 0, 0), r_wd = make_float4(0, 0, 1, 0), r_td = make_float4(0, 0, 1, 0), r_ti = make_float4(0, 0, 0, 0);
+#endif
+        bool unbounded = false;    // the query's tmax is infinite
         V3       o = v3(0, 0, 0), d = v3(0, 0, 1), idir = v3(0, 0, 0);    // the ray of the current level
         unsigned oct4 = 0, occ = 0;
-        float    tmin = 0.f, tmin_w = 0.f, tmax_w = 0.f;
+        float    tmin = 0.f;
         uint32_t node_off = 0, tri_off = 0, cur = 0;
         Hit      loc { 0.f, 0.f, 0.f, INVALID_PRIM };     // best inside the current instance
         Hit      best { 0.f, 0.f, 0.f, INVALID_PRIM };    // best overall: t (object space if RENORM), u, v, flat prim
@@ -639,9 +649,14 @@ namespace crb
                 local_next += need < avail ? need : avail;
                 if (!active && rank < avail)
                 {
+                    V3    wo, wd;
+                    float tmin_w, tmax_w;
                     source(base + rank, item, wo, wd, tmin_w, tmax_w);
-                    best     = Hit { tmax_w, 0.0f, 0.0f, INVALID_PRIM };
-                    best_key = tmax_w, best_k = MARK;
+                    r_wo      = make_float4(wo.x, wo.y, wo.z, tmin_w);
+                    r_wd      = make_float4(wd.x, wd.y, wd.z, tmax_w);
+                    unbounded = !(tmax_w < __int_as_float(0x7f800000));
+                    best      = Hit { tmax_w, 0.0f, 0.0f, INVALID_PRIM };
+                    best_key  = tmax_w, best_k = MARK;
                     if (sc.tlas.n_nodes == 0 || sc.n_inst == 0)
                     {
                         best.t   = __int_as_float(0x7f800000);
@@ -650,10 +665,12 @@ namespace crb
                     else
                     {
                         // TLAS traversal runs on the world ray, with a unit direction (t = world distance) when RENORM
-                        td     = RENORM ? normalize(wd) : wd;
-                        tidir  = v3(safe_rcp(td.x), safe_rcp(td.y), safe_rcp(td.z));
-                        toct   = make_oct4(td);
-                        o = wo, d = td, idir = tidir, oct4 = toct;
+                        const V3 td = RENORM ? normalize(wd) : wd;
+                        o = wo, d = td;
+                        idir   = v3(safe_rcp(td.x), safe_rcp(td.y), safe_rcp(td.z));
+                        oct4   = make_oct4(td);
+                        r_td   = make_float4(td.x, td.y, td.z, __uint_as_float(oct4));
+                        r_ti   = make_float4(idir.x, idir.y, idir.z, 0.0f);
                         tmin   = RENORM ? 0.0f : tmin_w;
                         node_off = 0, tri_off = 0, in_blas = false;
                         group  = make_uint2(0u, 0x80000000u);
@@ -696,7 +713,7 @@ namespace crb
                         {
                             const unsigned prim = __float_as_uint(a.w);
                             if (t < loc.t || prim < loc.prim) loc = Hit { t, u, v, prim };
-                            if (any && !(tmax_w < __int_as_float(0x7f800000)))
+                            if (any && unbounded)
                             {
                                 // an unbounded shadow ray: any triangle of any instance ends the query
                                 best = Hit { t, u, v, sc.inst[cur].flat_start + prim };
@@ -741,8 +758,9 @@ namespace crb
                                 stack[sp++] = make_uint2(MARK, 0u);
                                 cur = k;
                                 // model.cpp:107-112: inv * vec4(origin, 1), normalize(inv * vec4(direction, 0))
-                                o = xf34(inv, wo, 1.0f);
-                                d = xf34(inv, wd, 0.0f);
+                                const float4 qo = r_wo, qd = r_wd;
+                                o = xf34(inv, v3(qo.x, qo.y, qo.z), 1.0f);
+                                d = xf34(inv, v3(qd.x, qd.y, qd.z), 0.0f);
                                 if (RENORM) d = normalize(d);
                                 idir   = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
                                 oct4   = make_oct4(d);
@@ -785,6 +803,9 @@ namespace crb
                         {
                             const float4 *ip = reinterpret_cast<const float4 *>(sc.inst + cur);
                             float         key = loc.t;
+                            const float4  qo = r_wo;
+                            const V3      wo = v3(qo.x, qo.y, qo.z);
+                            const float   tmax_w = r_wd.w;
                             if (RENORM)
                             {
                                 const float4 f0 = __ldg(ip + 3), f1 = __ldg(ip + 4), f2 = __ldg(ip + 5);
@@ -799,8 +820,11 @@ namespace crb
                             }
                             loc.prim = INVALID_PRIM;
                         }
-                        o = wo, d = td, idir = tidir, oct4 = toct;
-                        tmin     = RENORM ? 0.0f : tmin_w;
+                        {
+                            const float4 qo = r_wo, qt = r_td, qi = r_ti;
+                            o = v3(qo.x, qo.y, qo.z), d = v3(qt.x, qt.y, qt.z), idir = v3(qi.x, qi.y, qi.z), oct4 = __float_as_uint(qt.w);
+                            tmin = RENORM ? 0.0f : qo.w;
+                        }
                         node_off = 0, tri_off = 0, in_blas = false;
                         continue;
                     }

@@ -822,7 +822,8 @@ namespace crb
 
         // ------------------------------------------------------------------ two-level variants of the two traversal kernels
 #ifndef CRB_TRACE2_OCC
-#define CRB_TRACE2_OCC 3    // resident CTAs per SM of the two-level traversal kernels (80 registers)
+#define CRB_TRACE2_OCC 4    // resident CTAs per SM of the two-level traversal kernels: 64 registers without spills since the TLAS-level ray
+                            // lives in shared memory (bvh8.cuh CRB_2L_SMEM); measured on config 4: 3 CTAs 2086-2115, 4 CTAs 2331 Mrays/s
 #endif
         template<bool COUNT>
         __global__ void __launch_bounds__(256, CRB_TRACE2_OCC) k_trace2(DScene sc, PathState ps)

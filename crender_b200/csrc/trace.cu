@@ -77,7 +77,7 @@ namespace crb
         // two-level scenes: the ray parameter t is invariant under the instance's affine map (no renormalisation for a
         // batch query with the caller's tnear/tfar), candidates are compared by t, ties go to the first (model, instance)
         template<bool COUNT, bool ANY>
-        __global__ void __launch_bounds__(256, 3) k_batch2(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits, uint8_t *__restrict__ occ,
+        __global__ void __launch_bounds__(256, 4) k_batch2(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits, uint8_t *__restrict__ occ,
                                                          uint32_t *cursor, unsigned long long *ctr)
         {
             TravCounters tc;
@@ -155,7 +155,7 @@ namespace crb
 #ifdef CRB_EMU
                 const unsigned g2 = 1;
 #else
-                const unsigned g2 = unsigned(s.n_sms) * 3;
+                const unsigned g2 = unsigned(s.n_sms) * 4;
 #endif
                 switch (mode)
                 {
