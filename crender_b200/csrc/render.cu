@@ -821,6 +821,9 @@ namespace crb
         }
 
         // ------------------------------------------------------------------ two-level variants of the two traversal kernels
+#ifndef CRB_TRACE2_STEPS
+#define CRB_TRACE2_STEPS TRACE_STEPS    // node iterations between two refill points of the two-level loop
+#endif
 #ifndef CRB_TRACE2_OCC
 #define CRB_TRACE2_OCC 4    // resident CTAs per SM of the two-level traversal kernels: 64 registers without spills since the TLAS-level ray
                             // lives in shared memory (bvh8.cuh CRB_2L_SMEM); measured on config 4: 3 CTAs 2086-2115, 4 CTAs 2331 Mrays/s
@@ -839,7 +842,7 @@ namespace crb
             auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
                 if (valid) ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
             };
-            trace_persistent_2l<COUNT, TRACE_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_TRACE, n, false, source, sink, &tc);
+            trace_persistent_2l<COUNT, CRB_TRACE2_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_TRACE, n, false, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES, tc.nodes);
@@ -868,7 +871,7 @@ namespace crb
                     ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
                 }
             };
-            trace_persistent_2l<COUNT, TRACE_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_SHADOW, n, true, source, sink, &tc);
+            trace_persistent_2l<COUNT, CRB_TRACE2_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_SHADOW, n, true, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES_SHADOW, tc.nodes);
