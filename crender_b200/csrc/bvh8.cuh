@@ -44,6 +44,13 @@
 #define CRB_EARLY_POP 2    // 1: +0.7 %, 2 (predicated in-place loads): +4.3 % (profiles/r1g_sweeps.md section 6)
 #endif
 
+// Per-lane state of the persistent trace loop that is touched rarely (the direction: leaf phase only; the winner's
+// barycentrics and the work item: at a hit / at retirement) lives in shared memory (CTAs of at most 256 threads, 8 KB):
+// the loop then fits 56 registers, i.e. 9 instead of 8 warps per scheduler (CTAs of 128 threads, 9 per SM).
+#ifndef CRB_TP_SMEM
+#define CRB_TP_SMEM 1
+#endif
+
 namespace crb
 {
     constexpr int      BVH8_STACK      = 48;     // entries; the builder rejects deeper trees loudly
@@ -362,11 +369,16 @@ namespace crb
         uint2          stack[BVH8_STACK];
         int            sp = 0;
         bool           active = false, finished = false, exhausted = false;
-        uint32_t       item = 0;
-        V3             o = v3(0, 0, 0), d = v3(0, 0, 1), idir = v3(0, 0, 0);
+#if CRB_TP_SMEM && !defined(CRB_EMU)
+        __shared__ float4 s_dir[256], s_win[256];    // (d, -) and (u, v, work item, -) of every lane of the CTA
+        float4 &r_dir = s_dir[threadIdx.x], &r_win = s_win[threadIdx.x];
+#else
+        float4 r_dir = make_float4(0, 0, 1, 0), r_win = make_float4(0, 0, 0, 0);
+#endif
+        V3             o = v3(0, 0, 0), idir = v3(0, 0, 0);
         unsigned       oct4 = 0, occ = 0;
-        float          tmin = 0.f;
-        Hit            best { 0.f, 0.f, 0.f, INVALID_PRIM };
+        float          tmin = 0.f, best_t = 0.f;
+        unsigned       best_prim = INVALID_PRIM;
         uint2          group = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
         uint32_t       local_next = 0, local_end = 0;
         // reservation granularity: large enough to keep the cursor atomic rare, small enough that the last
@@ -378,7 +390,10 @@ namespace crb
 
         for (;;)
         {
-            sink(finished, item, best);
+            {
+                const float4 w = r_win;
+                sink(finished, __float_as_uint(w.z), Hit { best_t, w.x, w.y, best_prim });
+            }
             finished = false;
 
             const unsigned idle = __ballot_sync(FULL, !active);
@@ -406,12 +421,16 @@ namespace crb
                     const uint32_t idx = base + rank;
                     if (rank < avail)
                     {
-                        float tmax;
+                        float    tmax;
+                        uint32_t item;
+                        V3       d;
                         source(idx, item, o, d, tmin, tmax);
-                        best = Hit { tmax, 0.0f, 0.0f, INVALID_PRIM };
+                        r_dir  = make_float4(d.x, d.y, d.z, 0.0f);
+                        r_win  = make_float4(0.0f, 0.0f, __uint_as_float(item), 0.0f);
+                        best_t = tmax, best_prim = INVALID_PRIM;
                         if (bvh.n_nodes == 0)
                         {
-                            best.t   = __int_as_float(0x7f800000);
+                            best_t   = __int_as_float(0x7f800000);
                             finished = true;
                         }
                         else
@@ -440,7 +459,7 @@ namespace crb
                     const uint4 *np = bvh.nodes + size_t(node_index) * 5;
                     const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                     if (COUNT) ctr->nodes++;
-                    node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, best.t, group, tgroup, occ);
+                    node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, best_t, group, tgroup, occ);
                 }
 #if CRB_EARLY_POP
                 // ---- pop BEFORE the leaf phase: a lane whose node group has no inner child left will need the next
@@ -475,12 +494,17 @@ namespace crb
                     {
                         const float4 *tp = bvh.tris + size_t(pop_triangle(tgroup, occ)) * 3;
                         const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
+                        const float4  dq = r_dir;
                         if (COUNT) ctr->tris++;
                         float t, u, v;
-                        if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, best.t, t, u, v))
+                        if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, v3(dq.x, dq.y, dq.z), tmin, best_t, t, u, v))
                         {
                             const unsigned prim = __float_as_uint(a.w);
-                            if (t < best.t || prim < best.prim) best = Hit { t, u, v, prim };
+                            if (t < best_t || prim < best_prim)
+                            {
+                                best_t = t, best_prim = prim;
+                                r_win.x = u, r_win.y = v;
+                            }
                             if (any)
                             {
                                 // any hit ends the query: drop all remaining work, the advance step below
@@ -497,12 +521,12 @@ namespace crb
                 {
 #if CRB_EARLY_POP
                     // the early pop found the stack empty (or an any-hit dropped everything): retire
-                    if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
+                    if (best_prim == INVALID_PRIM) best_t = __int_as_float(0x7f800000);
                     active = false, finished = true;
 #else
                     if (sp == 0)
                     {
-                        if (best.prim == INVALID_PRIM) best.t = __int_as_float(0x7f800000);
+                        if (best_prim == INVALID_PRIM) best_t = __int_as_float(0x7f800000);
                         active = false, finished = true;
                     }
                     else

@@ -236,12 +236,19 @@ namespace crb
         // ------------------------------------------------------------------ trace + material sort
         constexpr int TRACE_STEPS = 4;    // node iterations between two refill points of the persistent trace loop
 
-        // resident CTAs per SM of the two traversal kernels (4 = 64 registers; measured alternatives in profiles/)
+        // resident CTAs per SM and CTA size of the two traversal kernels
+        // With the rarely-touched lane state in shared memory (bvh8.cuh CRB_TP_SMEM) the loop compiles to 56 registers
+        // without spills: 9 CTAs of 128 threads per SM = 9 warps per scheduler. Measured on config 2 (profiles/r2_sweeps.md
+        // section 7): 256 x 4 (64 regs) 3468, 128 x 8 3451, 128 x 9 (56 regs) 3542, 128 x 10 (48 regs) 3535, 128 x 12 (40 regs,
+        // 72 B of spills) 3083 Mrays/s.
 #ifndef CRB_TRACE_OCC
-#define CRB_TRACE_OCC 4
+#define CRB_TRACE_OCC 9
+#endif
+#ifndef CRB_TRACE_BLOCK
+#define CRB_TRACE_BLOCK 128    // threads per CTA of the two single-level traversal kernels (at most 256: bvh8.cuh CRB_TP_SMEM)
 #endif
         template<bool COUNT, int STEPS>
-        __global__ void __launch_bounds__(256, CRB_TRACE_OCC) k_trace(DScene sc, PathState ps)
+        __global__ void __launch_bounds__(CRB_TRACE_BLOCK, CRB_TRACE_OCC) k_trace(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_IN];
             TravCounters   tc;
@@ -882,7 +889,7 @@ namespace crb
         // ------------------------------------------------------------------ K8 shadow rays
         // sun visibility without alpha cut-outs: any-hit through the persistent trace loop
         template<bool COUNT, int STEPS>
-        __global__ void __launch_bounds__(256, CRB_TRACE_OCC) k_shadow(DScene sc, PathState ps)
+        __global__ void __launch_bounds__(CRB_TRACE_BLOCK, CRB_TRACE_OCC) k_shadow(DScene sc, PathState ps)
         {
             const uint32_t n = ps.counters[CTR_SHADOW];
             TravCounters   tc;
@@ -1252,9 +1259,9 @@ namespace crb
         const bool count = (flags & CRB_RENDER_FLAG_COUNTERS) != 0;
         static const int steps = getenv("CRB_TRACE_STEPS") ? atoi(getenv("CRB_TRACE_STEPS")) : TRACE_STEPS;    // tuning knob
 #ifdef CRB_EMU
-        const unsigned pgrid = 1, pblock = 1, tgrid = 1, t2grid = 1, sgrid = 1, sblock = 1;
+        const unsigned pgrid = 1, pblock = 1, tgrid = 1, tblock = 1, t2grid = 1, sgrid = 1, sblock = 1;
 #else
-        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC, t2grid = unsigned(n_sms) * CRB_TRACE2_OCC,
+        const unsigned pgrid = unsigned(n_sms) * 4, pblock = 256, tgrid = unsigned(n_sms) * CRB_TRACE_OCC, tblock = CRB_TRACE_BLOCK, t2grid = unsigned(n_sms) * CRB_TRACE2_OCC,
                        sgrid = unsigned(n_sms) * (1024 / CRB_SHADE_BLOCK), sblock = CRB_SHADE_BLOCK;
         const Span span { take_event(), take_event() };
         CRB_CUDA_CHECK(cudaEventRecord(span.a, stream()));
@@ -1291,15 +1298,15 @@ namespace crb
                         CRB_LAUNCH((k_trace2<false>), t2grid, pblock, st, dscene, ps);
                 }
                 else if (count)
-                    CRB_LAUNCH((k_trace<true, TRACE_STEPS>), tgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<true, TRACE_STEPS>), tgrid, tblock, st, dscene, ps);
                 else if (steps == 1)
-                    CRB_LAUNCH((k_trace<false, 1>), tgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 1>), tgrid, tblock, st, dscene, ps);
                 else if (steps == 2)
-                    CRB_LAUNCH((k_trace<false, 2>), tgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 2>), tgrid, tblock, st, dscene, ps);
                 else if (steps == 8)
-                    CRB_LAUNCH((k_trace<false, 8>), tgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 8>), tgrid, tblock, st, dscene, ps);
                 else
-                    CRB_LAUNCH((k_trace<false, 4>), tgrid, pblock, st, dscene, ps);
+                    CRB_LAUNCH((k_trace<false, 4>), tgrid, tblock, st, dscene, ps);
                 tock();
                 tick(CRB_K_SHADE);
                 if (ps.sorted) CRB_LAUNCH(k_classify, pgrid, pblock, st, dscene, ps);
@@ -1327,15 +1334,15 @@ namespace crb
                             CRB_LAUNCH((k_shadow2<false>), t2grid, pblock, st, dscene, ps);
                     }
                     else if (count)
-                        CRB_LAUNCH((k_shadow<true, TRACE_STEPS>), tgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<true, TRACE_STEPS>), tgrid, tblock, st, dscene, ps);
                     else if (steps == 1)
-                        CRB_LAUNCH((k_shadow<false, 1>), tgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 1>), tgrid, tblock, st, dscene, ps);
                     else if (steps == 2)
-                        CRB_LAUNCH((k_shadow<false, 2>), tgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 2>), tgrid, tblock, st, dscene, ps);
                     else if (steps == 8)
-                        CRB_LAUNCH((k_shadow<false, 8>), tgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 8>), tgrid, tblock, st, dscene, ps);
                     else
-                        CRB_LAUNCH((k_shadow<false, 4>), tgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_shadow<false, 4>), tgrid, tblock, st, dscene, ps);
                     tock();
                     launches++;
                 }

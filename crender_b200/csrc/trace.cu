@@ -28,7 +28,7 @@ namespace crb
 
         // persistent kernels: each warp is a pool of 32 traversal lanes refilled from `cursor` (bvh8.cuh)
         template<bool COUNT>
-        __global__ void __launch_bounds__(256, 4) k_intersect_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits,
+        __global__ void __launch_bounds__(128, 9) k_intersect_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, crb_hit *__restrict__ hits,
                                                                  uint32_t *cursor, unsigned long long *ctr)
         {
             TravCounters tc;
@@ -54,7 +54,7 @@ namespace crb
         }
 
         template<bool COUNT>
-        __global__ void __launch_bounds__(256, 4) k_occluded_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, uint8_t *__restrict__ occ,
+        __global__ void __launch_bounds__(128, 9) k_occluded_batch(DScene sc, const float4 *__restrict__ rays, uint32_t n, uint8_t *__restrict__ occ,
                                                                 uint32_t *cursor, unsigned long long *ctr)
         {
             TravCounters tc;
@@ -147,22 +147,22 @@ namespace crb
 #ifdef CRB_EMU
             const unsigned g = 1, blk = 1;
 #else
-            const unsigned g = unsigned(s.n_sms) * 4, blk = 256;
+            const unsigned g = unsigned(s.n_sms) * 9, blk = 128;    // 56 registers: 9 warps per scheduler (render.cu CRB_TRACE_OCC)
 #endif
             dev_zero(cursor, 4, st);
             if (sc.two_level)
             {
 #ifdef CRB_EMU
-                const unsigned g2 = 1;
+                const unsigned g2 = 1, blk2 = 1;
 #else
-                const unsigned g2 = unsigned(s.n_sms) * 4;
+                const unsigned g2 = unsigned(s.n_sms) * 4, blk2 = 256;
 #endif
                 switch (mode)
                 {
-                case 0: CRB_LAUNCH((k_batch2<false, false>), g2, blk, st, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), (uint8_t *) nullptr, cursor, ctr); break;
-                case 1: CRB_LAUNCH((k_batch2<false, true>), g2, blk, st, sc, rp, cnt32, (crb_hit *) nullptr, reinterpret_cast<uint8_t *>(op), cursor, ctr); break;
-                case 2: CRB_LAUNCH((k_batch2<true, false>), g2, blk, st, sc, rp, cnt32, (crb_hit *) nullptr, (uint8_t *) nullptr, cursor, ctr); break;
-                default: CRB_LAUNCH((k_batch2<true, true>), g2, blk, st, sc, rp, cnt32, (crb_hit *) nullptr, (uint8_t *) nullptr, cursor, ctr); break;
+                case 0: CRB_LAUNCH((k_batch2<false, false>), g2, blk2, st, sc, rp, cnt32, reinterpret_cast<crb_hit *>(op), (uint8_t *) nullptr, cursor, ctr); break;
+                case 1: CRB_LAUNCH((k_batch2<false, true>), g2, blk2, st, sc, rp, cnt32, (crb_hit *) nullptr, reinterpret_cast<uint8_t *>(op), cursor, ctr); break;
+                case 2: CRB_LAUNCH((k_batch2<true, false>), g2, blk2, st, sc, rp, cnt32, (crb_hit *) nullptr, (uint8_t *) nullptr, cursor, ctr); break;
+                default: CRB_LAUNCH((k_batch2<true, true>), g2, blk2, st, sc, rp, cnt32, (crb_hit *) nullptr, (uint8_t *) nullptr, cursor, ctr); break;
                 }
                 return;
             }
