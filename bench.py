@@ -329,8 +329,8 @@ def run_ours(a):
         "config": {
             "workload": workload_name(a), "spp_per_step_per_gpu": spp, "total_spp": spp * a.steps * world, "partition": "spp" if world > 1 else "none",
             "merge": rinfo["merge"] if world > 1 else "none",
-            "l2_flush": "inputs larger than L2: %.1fM paths x 152 B path state (%.1f GB) + %.0f MB BVH stream through the 126 MB L2 every step"
-            % (a.width * a.height * spp / 1e6, a.width * a.height * spp * 152 / 1e9, (info.node_bytes + info.tri_bytes) / 1e6),
+            "l2_flush": "inputs larger than L2: %.1fM paths x 200 B path state (%.1f GB) + %.0f MB BVH stream through the 126 MB L2 every step"
+            % (a.width * a.height * spp / 1e6, a.width * a.height * spp * 200 / 1e9, (info.node_bytes + info.tri_bytes) / 1e6),
             "triangles": int(info.n_triangles), "bvh_nodes": int(info.n_nodes), "bvh_bytes": int(info.node_bytes + info.tri_bytes),
         },
         "samples_per_s": psamples / (ms * 1e-3), "ref_rays_per_s": ref_rays / (ms * 1e-3), "rays_per_sample": queries / max(1, psamples),

@@ -253,8 +253,8 @@ namespace crb
             const uint32_t n = ps.counters[CTR_IN];
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &slot, V3 &o, V3 &d, float &tmin, float &tmax) {
-                slot             = ps.q_in[idx];
-                const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                slot            = idx;    // the path records are in queue order: no indirection, coalesced loads
+                const float4 ro = ps.ray_o[idx], rd = ps.ray_d[idx];
                 o               = v3(ro.x, ro.y, ro.z);
                 d               = normalize(v3(rd.x, rd.y, rd.z));    // model.cpp:107-112: the query direction is normalised
                 tmin = 0.00001f, tmax = inf_f();                      // model.cpp:21-22
@@ -285,8 +285,8 @@ namespace crb
                 uint32_t       slot = 0;
                 if (idx < n)
                 {
-                    slot                = ps.q_in[idx];
-                    const uint32_t prim = __float_as_uint(ps.hit[slot].w);
+                    slot                = idx;    // the class queues hold RECORD indices
+                    const uint32_t prim = __float_as_uint(ps.hit[idx].w);
                     if (prim == INVALID_PRIM)
                         cls = 0;
                     else
@@ -398,22 +398,25 @@ namespace crb
                 bool           survive  = false, want_shadow = false;
                 uint32_t       slot     = 0;
                 ShadowRay      sr;
+                float4         out_o, out_d, out_t;    // the surviving path's next record, written at its place in the next queue
                 if (idx < n)
                 {
-                    int cls;
+                    int      cls;
+                    uint32_t rec;    // index of the path's record in the queue-ordered arrays
                     if (ps.sorted)
                     {
-                        cls  = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
-                        slot = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
+                        cls = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
+                        rec = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
                     }
                     else
                     {
-                        // unsorted mode: paths are shaded in queue (= screen) order
-                        slot = ps.q_in[idx];
-                        cls  = -1;
+                        // unsorted mode: paths are shaded in queue order, every load below is coalesced
+                        rec = idx;
+                        cls = -1;
                     }
-                    const float4 h4 = ld128_grouped(ps.hit + slot), ro = ld128_grouped(ps.ray_o + slot), rd = ld128_grouped(ps.ray_d + slot),
-                                 t4 = ld128_grouped(ps.thr + slot);
+                    slot            = ps.q_in[rec];
+                    const float4 h4 = ld128_grouped(ps.hit + rec), ro = ld128_grouped(ps.ray_o + rec), rd = ld128_grouped(ps.ray_d + rec),
+                                 t4 = ld128_grouped(ps.thr + rec);
                     prefetch_l2(ps.rad + slot);
                     if (cls < 0) cls = __float_as_uint(h4.w) == INVALID_PRIM ? 0 : 1;
                     const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
@@ -453,9 +456,9 @@ namespace crb
                         if (col.w == 0.0f)
                         {
                             // alpha cut-out: renderer.cpp:294-301 (steps 0.1 along the un-normalised direction)
-                            const V3 p     = sf.point + d * 0.1f;
-                            ps.ray_o[slot] = make_float4(p.x, p.y, p.z, 0.f);
-                            survive        = true;
+                            const V3 p = sf.point + d * 0.1f;
+                            out_o = make_float4(p.x, p.y, p.z, 0.f), out_d = rd, out_t = t4;
+                            survive = true;
                         }
                         else
                         {
@@ -511,10 +514,10 @@ namespace crb
                                 const V3     r  = v3(r4.x, r4.y, r4.z) + thr * mat.emission;
                                 ps.rad[slot]    = make_float4(r.x, r.y, r.z, 0.f);
                             }
-                            ps.thr[slot]    = make_float4(thr.x, thr.y, thr.z, 0.f);
-                            ps.ray_o[slot]  = make_float4(no.x, no.y, no.z, 0.f);
-                            ps.ray_d[slot]  = make_float4(nd.x, nd.y, nd.z, 0.f);
-                            survive         = true;
+                            out_t   = make_float4(thr.x, thr.y, thr.z, 0.f);
+                            out_o   = make_float4(no.x, no.y, no.z, 0.f);
+                            out_d   = make_float4(nd.x, nd.y, nd.z, 0.f);
+                            survive = true;
 
                             if (sc.sun.enabled)
                             {
@@ -544,7 +547,12 @@ namespace crb
                 const int  cidx[2] = { CTR_NEXT, CTR_SHADOW };
                 uint32_t   at[2];
                 block_reserve<2>(pred, ps.counters, cidx, at);
-                if (survive) ps.q_next[at[0]] = slot;
+                if (survive)
+                {
+                    // the next bounce's record, compacted: k_trace and the next k_shade stream it without indirection
+                    ps.q_next[at[0]]   = slot;
+                    ps.ray_o_next[at[0]] = out_o, ps.ray_d_next[at[0]] = out_d, ps.thr_next[at[0]] = out_t;
+                }
                 if (want_shadow) ps.shadow[at[1]] = sr;
             }
         }
@@ -599,21 +607,24 @@ namespace crb
                 bool           survive = false, want_shadow = false;
                 uint32_t       slot    = 0;
                 ShadowRay      sr;
+                float4         out_o, out_d, out_t;
                 if (idx < n)
                 {
-                    int cls;
+                    int      cls;
+                    uint32_t rec;
                     if (ps.sorted)
                     {
-                        cls  = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
-                        slot = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
+                        cls = idx < c0 ? 0 : (idx < c1 ? 1 : (idx < c2 ? 2 : 3));
+                        rec = ps.q_class[cls][idx - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)))];
                     }
                     else
                     {
-                        slot = ps.q_in[idx];
-                        cls  = -1;
+                        rec = idx;
+                        cls = -1;
                     }
-                    const float4 h4 = ld128_grouped(ps.hit + slot), ro = ld128_grouped(ps.ray_o + slot), rd = ld128_grouped(ps.ray_d + slot),
-                                 t4 = ld128_grouped(ps.thr + slot);
+                    slot            = ps.q_in[rec];
+                    const float4 h4 = ld128_grouped(ps.hit + rec), ro = ld128_grouped(ps.ray_o + rec), rd = ld128_grouped(ps.ray_d + rec),
+                                 t4 = ld128_grouped(ps.thr + rec);
                     prefetch_l2(ps.rad + slot);
                     if (cls < 0) cls = __float_as_uint(h4.w) == INVALID_PRIM ? 0 : 1;
                     const V3     o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
@@ -656,9 +667,9 @@ namespace crb
                         const float4    col = surface_colour(sc, mat, sf);
                         if (col.w == 0.0f)
                         {
-                            const V3 p     = sf.point + d * 0.1f;    // renderer.cpp:294-301
-                            ps.ray_o[slot] = make_float4(p.x, p.y, p.z, 0.f);
-                            survive        = true;
+                            const V3 p = sf.point + d * 0.1f;    // renderer.cpp:294-301
+                            out_o = make_float4(p.x, p.y, p.z, 0.f), out_d = rd, out_t = t4;
+                            survive = true;
                         }
                         else
                         {
@@ -788,10 +799,10 @@ namespace crb
                             if (!absorbed)
                             {
                                 const V3 t  = thr * weight;
-                                ps.thr[slot]   = make_float4(t.x, t.y, t.z, next_specular ? 1.f : 0.f);
-                                ps.ray_o[slot] = make_float4(no.x, no.y, no.z, 0.f);
-                                ps.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, 0.f);
-                                survive        = true;
+                                out_t   = make_float4(t.x, t.y, t.z, next_specular ? 1.f : 0.f);
+                                out_o   = make_float4(no.x, no.y, no.z, 0.f);
+                                out_d   = make_float4(nd.x, nd.y, nd.z, 0.f);
+                                survive = true;
                             }
                         }
                     }
@@ -800,7 +811,12 @@ namespace crb
                 const int  cidx[2] = { CTR_NEXT, CTR_SHADOW };
                 uint32_t   at[2];
                 block_reserve<2>(pred, ps.counters, cidx, at);
-                if (survive) ps.q_next[at[0]] = slot;
+                if (survive)
+                {
+                    // the next bounce's record, compacted: k_trace and the next k_shade stream it without indirection
+                    ps.q_next[at[0]]   = slot;
+                    ps.ray_o_next[at[0]] = out_o, ps.ray_d_next[at[0]] = out_d, ps.thr_next[at[0]] = out_t;
+                }
                 if (want_shadow) ps.shadow[at[1]] = sr;
             }
         }
@@ -841,8 +857,8 @@ namespace crb
             const uint32_t n = ps.counters[CTR_IN];
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &slot, V3 &o, V3 &d, float &tmin, float &tmax) {
-                slot            = ps.q_in[idx];
-                const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+                slot            = idx;
+                const float4 ro = ps.ray_o[idx], rd = ps.ray_d[idx];
                 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);    // as the reference holds it: every instance renormalises (model.cpp:110-112)
                 tmin = 0.00001f, tmax = inf_f();
             };
@@ -1127,6 +1143,7 @@ namespace crb
         if (n <= capacity) return;
         sync();
         ray_o.alloc(n), ray_d.alloc(n), thr.alloc(n), rad.alloc(n), hit.alloc(n);
+        ray_o2.alloc(n), ray_d2.alloc(n), thr2.alloc(n);
         q_in.alloc(n), q_next.alloc(n);
         for (auto &q : q_class) q.alloc(n);
         shadow.alloc(n);
@@ -1220,10 +1237,10 @@ namespace crb
         size_t         tpaths    = tp_env ? tp_env : target_paths;
 #ifndef CRB_EMU
         {
-            // never plan for more than a quarter of the free device memory (152 B of state per path)
+            // never plan for more than a quarter of the free device memory (200 B of state per path)
             const auto t_a = now();
             if (capacity == 0)
-                if (const size_t avail = dev_available_bytes()) mem_path_cap = std::max<size_t>(size_t(1) << 20, avail / 4 / 152);
+                if (const size_t avail = dev_available_bytes()) mem_path_cap = std::max<size_t>(size_t(1) << 20, avail / 4 / 200);
             if (mem_path_cap) tpaths = std::min(tpaths, mem_path_cap);
             ms_meminfo = ms_since(t_a);
         }
@@ -1238,6 +1255,7 @@ namespace crb
 
         PathState ps {};
         ps.ray_o = ray_o.p, ps.ray_d = ray_d.p, ps.thr = thr.p, ps.rad = rad.p, ps.hit = hit.p;
+        ps.ray_o_next = ray_o2.p, ps.ray_d_next = ray_d2.p, ps.thr_next = thr2.p;
         ps.q_in = q_in.p, ps.q_next = q_next.p;
         for (int c = 0; c < 4; c++) ps.q_class[c] = q_class[c].p;
         ps.shadow = shadow.p, ps.counters = counters.p, ps.stats = dstats.p;
@@ -1351,6 +1369,7 @@ namespace crb
                 tock();
                 launches++;
                 std::swap(ps.q_in, ps.q_next);
+                std::swap(ps.ray_o, ps.ray_o_next), std::swap(ps.ray_d, ps.ray_d_next), std::swap(ps.thr, ps.thr_next);
             }
 #ifdef CRB_EMU
             CRB_LAUNCH(k_accumulate, npix, 1, st, rp, ps);

@@ -12,17 +12,21 @@ namespace crb
         float4 c;    // rgb contribution added to the path if the light is visible
     };
 
-    // device pointers of the path-state SoA, indexed by path slot = sample_in_batch * npix + pixel
+    // device pointers of the path state. A path's identity is its slot = sample_in_batch * npix + pixel (radiance record,
+    // pixel, sample index); its per-bounce RECORD (ray, throughput, hit) lives at its position in the bounce's queue, so
+    // that every kernel streams the records of a bounce in order: k_shade writes the surviving paths' next records
+    // compacted into the *_next arrays, and the two sets are swapped after every bounce.
     struct PathState
     {
-        float4 *ray_o;    // xyz origin
-        float4 *ray_d;    // xyz direction exactly as the reference's cr::ray::direction (not re-normalised)
-        float4 *thr;      // xyz throughput, w = extended mode: previous vertex was specular
-        float4 *rad;      // xyz radiance ("final")
-        float4 *hit;      // t (normalised-direction units), u, v, flat prim (bits)
-        uint32_t *q_in;         // active path slots of this bounce
-        uint32_t *q_next;       // active path slots of the next bounce
-        uint32_t *q_class[4];   // after trace: 0 miss, 1 metal, 2 smooth, 3 glass (material sort)
+        float4 *ray_o;    // [queue position] xyz origin
+        float4 *ray_d;    // [queue position] xyz direction exactly as the reference's cr::ray::direction (not re-normalised)
+        float4 *thr;      // [queue position] xyz throughput, w = extended mode: previous vertex was specular
+        float4 *hit;      // [queue position] t (normalised-direction units), u, v, flat prim (bits)
+        float4 *ray_o_next, *ray_d_next, *thr_next;    // the next bounce's records
+        float4 *rad;      // [slot] xyz radiance ("final")
+        uint32_t *q_in;         // [queue position] path slot of this bounce's records
+        uint32_t *q_next;       // path slots of the next bounce's records
+        uint32_t *q_class[4];   // after trace: record indices by class: 0 miss, 1 metal, 2 smooth, 3 glass (material sort)
         ShadowRay *shadow;
         uint32_t  *counters;    // see CTR_* below
         unsigned long long *stats;    // see ST_* below
@@ -67,7 +71,7 @@ namespace crb
         DBuf<float4> accum, display, albedo, normal, depth;
         // path state
         size_t              capacity = 0;
-        DBuf<float4>        ray_o, ray_d, thr, rad, hit;
+        DBuf<float4>        ray_o, ray_d, thr, rad, hit, ray_o2, ray_d2, thr2;
         DBuf<uint32_t>      q_in, q_next, q_class[4];
         DBuf<ShadowRay>     shadow;
         DBuf<uint32_t>      counters;
@@ -77,7 +81,7 @@ namespace crb
         uint64_t launches  = 0;
         uint64_t pixel_samples = 0;
         // paths in flight per batch: bigger batches amortise kernel tails and keep the late, thin bounces
-        // wide enough for 148 SMs (swept in profiles/r1c_sweeps.md §10); 152 B of path state each
+        // wide enough for 148 SMs (swept in profiles/r1c_sweeps.md §10); 200 B of path state each
         size_t   target_paths = size_t(1) << 25;
         size_t   mem_path_cap = 0;
         double   kernel_ms[8]    = {};
