@@ -36,9 +36,10 @@ namespace crb
         constexpr float INV_TAU_F = 1.0f / 6.28318530717f;    // :24
 
         // ---- counter-based sampler (replaces the thread_local mt19937 of renderer.cpp:6-11, which is
-        // default-seeded per worker thread and not reproducible). key = f(seed, pixel, sample);
-        // u(dim) = top 24 bits of mix(key + dim*golden). dims: 0,1 jitter; 2+4i+{0,1} scatter of bounce
-        // i; 2+4i+{2,3} sun cone sample of bounce i.
+        // default-seeded per worker thread and not reproducible). The key is two independent 32-bit hashes of
+        // (seed, pixel, sample) - no two paths of a frame share a stream; u(dim) = top 24 bits of
+        // mix(mix(k1 + dim*golden) ^ k2). dims: 0,1 jitter; 2+4i+{0,1} scatter of bounce i; 2+4i+{2,3} sun cone
+        // sample of bounce i.
         __device__ __forceinline__ uint32_t mix32(uint32_t x)
         {
             x ^= x >> 16;
@@ -48,14 +49,21 @@ namespace crb
             x ^= x >> 16;
             return x;
         }
-        __device__ __forceinline__ uint32_t path_key(uint32_t seed, uint32_t pixel, uint32_t sample)
+        struct PathKey
         {
-            return mix32(mix32(mix32(seed + 0x9e3779b9u) ^ pixel) ^ sample);
+            uint32_t k1, k2;
+        };
+        __device__ __forceinline__ PathKey path_key(uint32_t seed, uint32_t pixel, uint32_t sample)
+        {
+            return PathKey { mix32(mix32(mix32(seed + 0x9e3779b9u) ^ pixel) ^ sample), mix32(mix32(mix32(seed + 0x85ebca6bu) ^ sample) ^ pixel) };
         }
-        __device__ __forceinline__ float rnd(uint32_t key, uint32_t dim) { return float(mix32(key + dim * 0x9e3779b9u) >> 8) * (1.0f / 16777216.0f); }
+        __device__ __forceinline__ float rnd(PathKey key, uint32_t dim)
+        {
+            return float(mix32(mix32(key.k1 + dim * 0x9e3779b9u) ^ key.k2) >> 8) * (1.0f / 16777216.0f);
+        }
 
         // a caller-supplied sample table (crb_render_set_sample_table) replaces the hash: [sample][pixel][dimension]
-        __device__ __forceinline__ float rnd_dim(const RenderParams &rp, uint32_t key, uint32_t pixel, uint32_t sample, uint32_t dim)
+        __device__ __forceinline__ float rnd_dim(const RenderParams &rp, PathKey key, uint32_t pixel, uint32_t sample, uint32_t dim)
         {
             if (rp.table && sample < rp.table_samples && dim < rp.table_dims)
                 return rp.table[(size_t(sample) * rp.w * rp.h + pixel) * rp.table_dims + dim];
@@ -190,7 +198,7 @@ namespace crb
             const uint32_t pix = slot % rp.npix, s = slot / rp.npix;
             const uint32_t x = pix % rp.w, y = row_of(rp, pix / rp.w);
             const uint32_t sample = rp.first_sample + s;
-            const uint32_t key    = path_key(rp.seed, x + y * rp.w, sample);
+            const PathKey  key    = path_key(rp.seed, x + y * rp.w, sample);
             const float    fx = (float(x) + rnd_dim(rp, key, x + y * rp.w, sample, 0)) / float(rp.w),
                            fy = (float(y) + rnd_dim(rp, key, x + y * rp.w, sample, 1)) / float(rp.h);    // renderer.cpp:260-263
             const DCamera &c = sc.cam;
@@ -490,7 +498,7 @@ namespace crb
                             else
                             {
                                 // renderer.cpp:92-98, sampling.h:168-172
-                                const uint32_t key = path_key(rp.seed, x + y * rp.w, sample);
+                                const PathKey  key = path_key(rp.seed, x + y * rp.w, sample);
                                 const V3       h   = sf.normal + sample_sphere(rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i), rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i + 1));
                                 no                 = sf.point + sf.normal * 0.0001f;
                                 nd                 = normalize(h);
@@ -522,7 +530,7 @@ namespace crb
                             if (sc.sun.enabled)
                             {
                                 // renderer.cpp:316-329,348-353; sampling.h:53-57,72-80
-                                const uint32_t key = path_key(rp.seed, x + y * rp.w, sample);
+                                const PathKey  key = path_key(rp.seed, x + y * rp.w, sample);
                                 const V3       so  = sf.point + sf.normal * 0.001f;
                                 const V3       l   = map_to_solid_angle(rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i + 2), rnd_dim(rp, key, x + y * rp.w, sample, 2 + 4 * i + 3), sc.sun.one_minus_cos);
                                 const float   *T   = sc.sun.transform;
@@ -634,7 +642,7 @@ namespace crb
                     const uint32_t x = pix % rp.w, y = row_of(rp, pix / rp.w);
                     const uint32_t sample = rp.first_sample + s;
                     const bool     aov    = (i == 0) && (sample == rp.aov_sample);
-                    const uint32_t key    = path_key(rp.seed, x + y * rp.w, sample);
+                    const PathKey  key    = path_key(rp.seed, x + y * rp.w, sample);
                     const uint32_t dim    = 2 + 6 * i;
                     const V3       dn     = normalize(d);
 

@@ -28,7 +28,8 @@ def test_randf_stream_is_mt19937_default_seed(oracle):
 
 
 def test_counter_rng_spec(oracle):
-    # DESIGN.md "Sampler": lowbias32 finaliser, key = mix(mix(mix(seed+phi)^pixel)^sample), 24-bit mantissa
+    # DESIGN.md "Sampler": lowbias32 finaliser, two 32-bit keys k1 = mix(mix(mix(seed+phi)^pixel)^sample),
+    # k2 = mix(mix(mix(seed+0x85ebca6b)^sample)^pixel), u = mix(mix(k1+dim*phi)^k2), 24-bit mantissa
     def mix(x):
         x &= 0xFFFFFFFF
         x ^= x >> 16
@@ -40,8 +41,9 @@ def test_counter_rng_spec(oracle):
 
     L = oracle.lib()
     for seed, pix, smp, dim in [(0, 0, 0, 0), (3, 12345, 7, 5), (0xFFFFFFFF, 2073599, 255, 33)]:
-        key = mix(mix(mix((seed + 0x9E3779B9) & 0xFFFFFFFF) ^ pix) ^ smp)
-        u = (mix((key + dim * 0x9E3779B9) & 0xFFFFFFFF) >> 8) / 16777216.0
+        k1 = mix(mix(mix((seed + 0x9E3779B9) & 0xFFFFFFFF) ^ pix) ^ smp)
+        k2 = mix(mix(mix((seed + 0x85EBCA6B) & 0xFFFFFFFF) ^ smp) ^ pix)
+        u = (mix(mix((k1 + dim * 0x9E3779B9) & 0xFFFFFFFF) ^ k2) >> 8) / 16777216.0
         assert L.orc_kat_rng(seed, pix, smp, dim) == np.float32(u)
     us = np.asarray([L.orc_kat_rng(1, i, 0, 0) for i in range(20000)])
     assert 0.0 <= us.min() and us.max() < 1.0 and abs(us.mean() - 0.5) < 0.01
