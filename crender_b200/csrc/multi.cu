@@ -103,7 +103,7 @@ namespace crb
 
         // K10 fused: the collective and the resolve as ONE kernel over peer memory. This GPU owns pixels [lo, hi); it
         // pulls them from every rank's snapshot (NVLink loads, 16 bytes per lane, coalesced), sums in rank order
-        // (spp partition) or takes the owner's value (tile partition: flipped row -> sample row -> 64-row band ->
+        // (spp partition) or takes the owner's value (tile partition: flipped row -> sample row -> row band ->
         // band % world), resolves, and stores sum + display into the root's merged buffers.
         __global__ void __launch_bounds__(256) k_merge_peers(const float4 *const *__restrict__ stage, int world, int tile, uint32_t w, uint32_t h, uint32_t lo,
                                                              uint32_t hi, float4 *__restrict__ merged_root, float4 *__restrict__ display_root)

@@ -7,7 +7,7 @@
 //
 //   scene + BVH     replicated: one crb::Scene per GPU, committed on that GPU (the device build is deterministic)
 //   work            partitioned by SAMPLE INDEX (PARTITION_SPP: rank g renders a contiguous share of every
-//                   crb_render_samples range, BASELINE config 4) or by interleaved 64-ROW BANDS (PARTITION_TILE,
+//                   crb_render_samples range, BASELINE config 4) or by interleaved 16-ROW BANDS (PARTITION_TILE,
 //                   BASELINE config 5); the sampler is keyed by global pixel and sample, so the union over ranks is
 //                   the single-GPU set of paths
 //   merge ("flush") snapshot of every rank's float4 accumulator (device-to-device on the render stream), then on a
@@ -38,7 +38,10 @@
 namespace crb
 {
     enum { PARTITION_SPP = 0, PARTITION_TILE = 1 };
-    constexpr uint32_t TILE_BAND_ROWS = 64;    // BASELINE config 5: "interleaved 64-row tile bands"
+    // Height of the interleaved row bands of the tile partition. 16 rows: a 2160-row frame is 135 bands, i.e. 17 or 16 per GPU
+    // on 8 GPUs (row-count imbalance 0.7 %) and the 128-row period is short against the image content; with the 64 rows of
+    // SURVEY.md's example the same frame is 34 bands (5 or 4 per GPU) and config 5 scaled at 0.82 on 8 GPUs (profiles/r2q).
+    constexpr uint32_t TILE_BAND_ROWS = 16;
 
     // contiguous share [lo, hi) of `n` samples starting at `first` for `rank` of `world` (earlier ranks take the remainder)
     inline void sample_share(uint32_t rank, uint32_t world, uint32_t first, uint32_t n, uint32_t &lo, uint32_t &hi)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box call (run through gpurun): tools/gpu_call.sh <tag> <what>...   what = smoke | tests | sanitize | anchor | bench | benchq | ref | launches | ncu_trace | ncu_shade | ncu_c4 | ncu_c4flat | multi
+# One GPU-box call (run through gpurun): tools/gpu_call.sh <tag> <what>...   what = smoke | tests | sanitize | anchor | bench | benchq | ref | launches | ncu_trace | ncu_shade | ncu_c4 | ncu_c4flat | multi | multi48
 # Everything lands under gpurun_out/<tag>_* (the box returns at most 64 MiB per call: at most two ncu_* steps per call); summaries for profiles/ are made afterwards in the development container
 # (tools/ncu_summary.py). Each step has its own timeout so that a hang cannot take the box.
 tag=$1; shift
@@ -25,6 +25,10 @@ for what in "$@"; do
                if [ $g -eq 1 ]; then timeout 600 python bench.py --no-cpu-baseline > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
                else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 2960$g bench.py --gpus $g > $out/${tag}_bench_n$g.json 2> $out/${tag}_bench_n$g.err; fi
                tail -c 900 $out/${tag}_bench_n$g.json; tail -2 $out/${tag}_bench_n$g.err
+             done ;;
+    multi48) for g in 4 8; do
+               timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 2961$g bench.py --gpus $g --only c4,c5 --no-roofline > $out/${tag}_bench_n$g.json 2> $out/${tag}_bench_n$g.err
+               tail -c 600 $out/${tag}_bench_n$g.json; tail -2 $out/${tag}_bench_n$g.err
              done ;;
     *) echo "unknown step $what" ;;
   esac
