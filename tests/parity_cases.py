@@ -780,3 +780,21 @@ def check_two_level_edge_cases(oracle, lib_path):
         ro = oracle.renderer(w, h, 4, o, seed=1)
         ro.render(2)
         assert common.relrmse(rg.raw_sum()[..., :3], ro.raw_sum()[..., :3]) <= IMG_RELRMSE, name
+
+
+def check_tiny_models(oracle, lib_path):
+    """Models of 1..8 triangles take the single-node build (bvh_build.cu k_tiny_bvh), 9 and more the full pipeline: hits of
+    random small triangle soups against the oracle, every field equal; as a flat scene and as an instanced model."""
+    rs = np.random.RandomState(5)
+    for n in (1, 2, 3, 5, 7, 8, 9, 17):
+        tris = (rs.uniform(-1, 1, (n, 1, 3)) + rs.uniform(-0.6, 0.6, (n, 3, 3))).astype(np.float32)
+        for inst in (None, np.stack([np.eye(4, dtype=np.float32), scenes.translation(2.5, 0.0, 0.5)]).astype(np.float32)):
+            desc = scenes.SceneDesc(f"tiny{n}", [scenes.MeshDesc(tris, np.zeros(n, np.uint32), [material()], instances=inst, name="soup")],
+                                    api.camera(position=(0.0, 0.0, -6.0), fov=50.0))
+            o, g = build_pair(oracle, lib_path, desc)
+            rays = common.mixed_rays(desc, 4000, seed=31 + n)
+            ho, hg = o.cast_rays(rays), g.cast_rays(rays)
+            assert (ho["prim"] != common.MISS).sum() > 50, n
+            for f in ("prim", "model", "inst", "t", "u", "v"):
+                np.testing.assert_array_equal(hg[f], ho[f], err_msg=f"n={n} {f}")
+            np.testing.assert_array_equal(g.occluded(rays).astype(bool), hg["prim"] != common.MISS)

@@ -83,3 +83,7 @@ def test_target_spp(emu_lib):
 
 def test_two_level_edge_cases(oracle, emu_lib):
     pc.check_two_level_edge_cases(oracle, emu_lib)
+
+
+def test_tiny_models(oracle, emu_lib):
+    pc.check_tiny_models(oracle, emu_lib)

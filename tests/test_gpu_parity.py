@@ -216,6 +216,10 @@ def test_two_level_edge_cases(oracle, product_lib):
     pc.check_two_level_edge_cases(oracle, product_lib)
 
 
+def test_tiny_models(oracle, product_lib):
+    pc.check_tiny_models(oracle, product_lib)
+
+
 def test_against_golden_fixtures(product_lib):
     """The CUDA path against the committed fixtures (no oracle at run time for this test)."""
     import os
