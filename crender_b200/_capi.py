@@ -132,6 +132,7 @@ SIGNATURES = {
     "crb_render_resolve": (C.c_int, [_P]),
     "crb_render_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "crb_render_set_bands": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "crb_render_set_bands_ordered": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "crb_render_create_multi": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "crb_comm_unique_id": (C.c_int, [_P]),
     "crb_render_create_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),

@@ -337,9 +337,13 @@ class renderer:
     def set_rows(self, y0: int, y1: int):
         _capi.check(self._lib, self._lib.crb_render_set_rows(self._h, y0, y1))
 
-    def set_bands(self, band_rows: int, first: int, stride: int):
-        """Interleaved row bands first, first+stride, ... of band_rows rows each, rendered as one launch sequence."""
-        _capi.check(self._lib, self._lib.crb_render_set_bands(self._h, band_rows, first, stride))
+    def set_bands(self, band_rows: int, first: int, stride: int, serpentine: bool = False):
+        """Interleaved row bands first, first+stride, ... of band_rows rows each, rendered as one launch sequence
+        (serpentine: the owner order is reversed in every other period of `stride` bands, as the library's tile partition does)."""
+        if serpentine:
+            _capi.check(self._lib, self._lib.crb_render_set_bands_ordered(self._h, band_rows, first, stride, 1))
+        else:
+            _capi.check(self._lib, self._lib.crb_render_set_bands(self._h, band_rows, first, stride))
 
     def set_sample_table(self, table: Optional[np.ndarray]):
         """A caller-supplied sample table float32 [n_samples, h*w, dims] replaces the hash sampler (ref-exact mode):

@@ -394,6 +394,13 @@ int crb_render_set_bands(crb_render *r, uint32_t band_rows, uint32_t first, uint
         h.r->set_bands(band_rows, first, stride);
     });
 }
+int crb_render_set_bands_ordered(crb_render *r, uint32_t band_rows, uint32_t first, uint32_t stride, int serpentine)
+{
+    return on_render(r, [&](crb_render &h) {
+        single_only(h, "crb_render_set_bands_ordered");
+        h.r->set_bands(band_rows, first, stride, serpentine != 0);
+    });
+}
 int crb_render_samples(crb_render *r, uint32_t first, uint32_t n)
 {
     return on_render(r, [&](crb_render &h) {

@@ -104,7 +104,7 @@ namespace crb
         // K10 fused: the collective and the resolve as ONE kernel over peer memory. This GPU owns pixels [lo, hi); it
         // pulls them from every rank's snapshot (NVLink loads, 16 bytes per lane, coalesced), sums in rank order
         // (spp partition) or takes the owner's value (tile partition: flipped row -> sample row -> row band ->
-        // band % world), resolves, and stores sum + display into the root's merged buffers.
+        // band_owner()), resolves, and stores sum + display into the root's merged buffers.
         __global__ void __launch_bounds__(256) k_merge_peers(const float4 *const *__restrict__ stage, int world, int tile, uint32_t w, uint32_t h, uint32_t lo,
                                                              uint32_t hi, float4 *__restrict__ merged_root, float4 *__restrict__ display_root)
         {
@@ -114,7 +114,7 @@ namespace crb
                 if (tile)
                 {
                     const uint32_t y = h - 1 - i / w;
-                    a                = stage[(y / TILE_BAND_ROWS) % uint32_t(world)][i];
+                    a                = stage[band_owner(y / TILE_BAND_ROWS, uint32_t(world), TILE_SERPENTINE)][i];
                 }
                 else
                 {
@@ -392,7 +392,7 @@ namespace crb
     void MultiRender::setup_partition(Local &l)
     {
         if (partition == PARTITION_TILE && world > 1)
-            l.render->set_bands(TILE_BAND_ROWS, uint32_t(l.rank), uint32_t(world));
+            l.render->set_bands(TILE_BAND_ROWS, uint32_t(l.rank), uint32_t(world), TILE_SERPENTINE != 0);
         else
             l.render->set_rows(0, h);
     }
@@ -575,7 +575,7 @@ namespace crb
         }
         else
         {
-            // all-gather of the interleaved row bands: band b is broadcast by its owner b % world. In the x/y-flipped
+            // all-gather of the interleaved row bands: band b is broadcast by its owner (band_owner). In the x/y-flipped
             // buffer the sample rows [y0,y1) are the contiguous rows [h-y1, h-y0).
             nccl_check(api.GroupStart(), "ncclGroupStart");
             uint32_t b = 0;
@@ -584,7 +584,7 @@ namespace crb
                 const uint32_t y1 = std::min(h, y0 + TILE_BAND_ROWS);
                 const size_t   off = size_t(h - y1) * w, cnt = size_t(y1 - y0) * w;
                 for (auto &lp : locals)
-                    nccl_check(api.Broadcast(lp->stage[k].p + off, lp->merged.p + off, cnt * 4, NCCL_FLOAT, int(b % uint32_t(world)), lp->comm, lp->comm_stream),
+                    nccl_check(api.Broadcast(lp->stage[k].p + off, lp->merged.p + off, cnt * 4, NCCL_FLOAT, int(band_owner(b, uint32_t(world), TILE_SERPENTINE)), lp->comm, lp->comm_stream),
                                "ncclBroadcast");
             }
             nccl_check(api.GroupEnd(), "ncclGroupEnd");
@@ -714,7 +714,7 @@ namespace crb
                 {
                     const uint32_t y1 = std::min(h, y0 + TILE_BAND_ROWS);
                     const size_t   off = size_t(h - y1) * w, cnt = size_t(y1 - y0) * w;
-                    Local         &o   = *locals[b % uint32_t(world)];
+                    Local         &o   = *locals[band_owner(b, uint32_t(world), TILE_SERPENTINE)];
 #ifdef CRB_EMU
                     memcpy(r.aov_stage.p + off, buf(o) + off, cnt * 16);
 #else
@@ -739,7 +739,7 @@ namespace crb
             {
                 const uint32_t y1 = std::min(h, y0 + TILE_BAND_ROWS);
                 const size_t   off = size_t(h - y1) * w, cnt = size_t(y1 - y0) * w;
-                nccl_check(api.Broadcast(buf(r) + off, r.aov_stage.p + off, cnt * 4, NCCL_FLOAT, int(b % uint32_t(world)), r.comm, r.comm_stream), "ncclBroadcast");
+                nccl_check(api.Broadcast(buf(r) + off, r.aov_stage.p + off, cnt * 4, NCCL_FLOAT, int(band_owner(b, uint32_t(world), TILE_SERPENTINE)), r.comm, r.comm_stream), "ncclBroadcast");
             }
         }
         nccl_check(api.GroupEnd(), "ncclGroupEnd");

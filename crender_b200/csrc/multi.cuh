@@ -42,6 +42,7 @@ namespace crb
     // on 8 GPUs (row-count imbalance 0.7 %) and the 128-row period is short against the image content; with the 64 rows of
     // SURVEY.md's example the same frame is 34 bands (5 or 4 per GPU) and config 5 scaled at 0.82 on 8 GPUs (profiles/r2q).
     constexpr uint32_t TILE_BAND_ROWS = 16;
+    constexpr uint32_t TILE_SERPENTINE = 1;    // owner order reversed in every other period of bands (render.cuh band_owner)
 
     // contiguous share [lo, hi) of `n` samples starting at `first` for `rank` of `world` (earlier ranks take the remainder)
     inline void sample_share(uint32_t rank, uint32_t world, uint32_t first, uint32_t n, uint32_t &lo, uint32_t &hi)

@@ -182,7 +182,7 @@ namespace crb
         {
             if (rp.band == 0) return rp.row0 + r;
             const uint32_t b = r / rp.band;
-            return (b * rp.band_stride + rp.band_first) * rp.band + (r - b * rp.band);
+            return (b * rp.band_stride + band_slot(b, rp.band_first, rp.band_stride, rp.band_serp)) * rp.band + (r - b * rp.band);
         }
 
         __device__ __forceinline__ uint32_t flipped_index(const RenderParams &rp, uint32_t x, uint32_t y)
@@ -1129,13 +1129,19 @@ namespace crb
         band = 0;
     }
 
-    void Render::set_bands(uint32_t band_rows, uint32_t first, uint32_t stride)
+    void Render::set_bands(uint32_t band_rows, uint32_t first, uint32_t stride, bool serpentine)
     {
         if (band_rows == 0 || stride == 0 || first >= stride) throw Error(ERR_INVALID_ARG, "set_bands: need band_rows > 0 and first < stride");
+        // this handle's band of period p is p * stride + band_slot(p): only the last period can lack it, so the local band
+        // index is the period and the (possibly partial) last band of the frame is its owner's last local band
         uint32_t rows = 0;
-        for (uint32_t y0 = first * band_rows; y0 < h; y0 += stride * band_rows) rows += std::min(band_rows, h - y0);
+        for (uint32_t p = 0; uint64_t(p) * stride * band_rows < h; p++)
+        {
+            const uint64_t y0 = (uint64_t(p) * stride + band_slot(p, first, stride, serpentine ? 1u : 0u)) * band_rows;
+            if (y0 < h) rows += uint32_t(std::min<uint64_t>(band_rows, h - y0));
+        }
         // rows == 0 is legal: more ranks than bands, this rank renders nothing
-        band = band_rows, band_first = first, band_stride = stride, band_nrows = rows;
+        band = band_rows, band_first = first, band_stride = stride, band_nrows = rows, band_serp = serpentine ? 1u : 0u;
         row0 = 0, row1 = h;
     }
 
@@ -1277,7 +1283,7 @@ namespace crb
 
         RenderParams rp {};
         rp.w = w, rp.h = h, rp.row0 = row0, rp.nrows = nrows, rp.npix = npix, rp.seed = seed;
-        rp.band = band, rp.band_first = band_first, rp.band_stride = band_stride;
+        rp.band = band, rp.band_first = band_first, rp.band_stride = band_stride, rp.band_serp = band_serp;
         rp.table = sample_table.p, rp.table_samples = sample_table.p ? table_samples : 0u, rp.table_dims = table_dims;
         rp.aov_sample = first + n - 1;
         rp.accum = accum.p, rp.display = display.p, rp.albedo = albedo.p, rp.normal = normal.p, rp.depth = depth.p;

@@ -44,6 +44,20 @@ namespace crb
         return make_float4(powf(clampf(a.x / n, 0.0f, 1.0f), g), powf(clampf(a.y / n, 0.0f, 1.0f), g), powf(clampf(a.z / n, 0.0f, 1.0f), g), 1.0f);
     }
 
+    // Tile partition, owner of the bands: period p = bands [p*stride, (p+1)*stride). Plain interleave gives slot j of every
+    // period to rank j; the serpentine order reverses every other period, which cancels a cost gradient along the image
+    // rows (measured on the 4K config-5 frame, 8 ranks, 16-row bands: max/mean of the ranks' times 1.049 plain — rank 0
+    // always the slowest, rank 7 the fastest — see profiles/r2_sweeps.md section 9).
+    __host__ __device__ inline uint32_t band_slot(uint32_t period, uint32_t first, uint32_t stride, uint32_t serpentine)
+    {
+        return (serpentine && (period & 1u)) ? stride - 1u - first : first;
+    }
+    __host__ __device__ inline uint32_t band_owner(uint32_t b, uint32_t world, uint32_t serpentine)
+    {
+        const uint32_t p = b / world, j = b % world;
+        return (serpentine && (p & 1u)) ? world - 1u - j : j;
+    }
+
     struct RenderParams
     {
         uint32_t w, h, row0, nrows, npix;    // npix = w * nrows (pixels rendered per pass)
@@ -52,6 +66,7 @@ namespace crb
         uint32_t aov_sample;                 // global sample index whose first hit is written to the AOVs
         uint32_t bounce;
         uint32_t band, band_first, band_stride;    // band != 0: local rows are interleaved bands (tile partition), see row_of()
+        uint32_t band_serp;                        // 1: the owner order is reversed in every other period (band_slot())
         float4  *accum, *display, *albedo, *normal, *depth;
         const float *table;    // caller-supplied sample table [table_samples][w*h][table_dims] or nullptr
         uint32_t     table_samples, table_dims;
@@ -63,6 +78,7 @@ namespace crb
         uint32_t w, h, max_bounces, seed, flags;
         uint32_t row0, row1;
         uint32_t band = 0, band_first = 0, band_stride = 1, band_nrows = 0;    // set_bands(): interleaved row bands instead of [row0,row1)
+        uint32_t band_serp = 0;
         uint32_t passes = 0;     // whole-frame passes completed (_current_sample): pass_px / (w*h)
         uint64_t pass_px = 0;    // pixel-samples accumulated (incl. a restored checkpoint's)
         uint64_t scene_version = ~0ull;
@@ -124,7 +140,7 @@ namespace crb
         void reset();
         void set_resolution(uint32_t w, uint32_t h);
         void set_rows(uint32_t y0, uint32_t y1);
-        void set_bands(uint32_t band_rows, uint32_t first, uint32_t stride);
+        void set_bands(uint32_t band_rows, uint32_t first, uint32_t stride, bool serpentine = false);
         void refresh();
         void render_samples(uint32_t first, uint32_t n);
         void sync();

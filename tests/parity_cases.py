@@ -146,6 +146,14 @@ def check_partition_invariance(lib_path, desc, w, h, spp, bounces):
         r.render(spp, first_sample=0)
     np.testing.assert_array_equal(r.raw_sum(), whole)
     np.testing.assert_array_equal(r.current_progress(), disp)
+    # the same with the serpentine owner order of the library's own tile partition (every other period reversed), for rank
+    # counts that leave the last period partial and band heights that leave the last band partial
+    for band, world in ((7, 3), (5, 4), (h, 2), (1, 5)):
+        r.start()
+        for first in range(world):
+            r.set_bands(band, first, world, serpentine=True)
+            r.render(spp, first_sample=0)
+        np.testing.assert_array_equal(r.raw_sum(), whole, err_msg=f"serpentine bands {band} x {world}")
     # linearity of the accumulation: rendering spp twice from the same first sample doubles the sum
     r.set_rows(0, h)
     r.start()
