@@ -23,7 +23,7 @@ Extra objects in the same line, measured at EVERY N (the multi-GPU workloads BAS
 object's `workload`):
   strong_c4 : config 4 — 18M flattened triangles (instanced terrain + city), 1080p, 1024 spp split into contiguous
               sample ranges across the N GPUs (STRONG scaling), one merge per flush;
-  tile_c5   : config 5 — 1M mesh + 64 emitters, 3840x2160, extended shading (area-light NEE), interleaved 16-row bands
+  tile_c5   : config 5 — 1M mesh + 64 emitters, 3840x2160, extended shading (area-light NEE), interleaved 8-row bands (serpentine owner order)
               across the N GPUs, all-gather merge, BVH build ms;
   c3_batch  : (N = 1) config 3 — 100M-ray closest-hit / occlusion batches on the 1M-triangle BVH, device-resident and
               through host pointers (chunked upload / trace / download pipeline).
@@ -624,7 +624,7 @@ def tile_c5(a, ctx, api, scenes, D):
     spp = a.c5_spp or (4096 if ctx.world >= 8 else 1024)
     desc = scenes.lights_scene(1000, 500, n_lights=64)
     label = (f"config5: 1M-triangle mesh + 64 emissive quads, 3840x2160, depth 8, extended shading (area-light + sun NEE), {spp} spp"
-             + ("" if spp == 4096 else " (bounded sample of the config's 4096)") + ", interleaved 16-row bands over the GPUs (tile partition), all-gather merge per call")
+             + ("" if spp == 4096 else " (bounded sample of the config's 4096)") + ", interleaved 8-row bands (serpentine owner order) over the GPUs (tile partition), all-gather merge per call")
     return partitioned_config(a, ctx, api, scenes, D, desc, 3840, 2160, 8, spp, 8, "tile", True, label, False)
 
 

@@ -7,7 +7,7 @@
 //
 //   scene + BVH     replicated: one crb::Scene per GPU, committed on that GPU (the device build is deterministic)
 //   work            partitioned by SAMPLE INDEX (PARTITION_SPP: rank g renders a contiguous share of every
-//                   crb_render_samples range, BASELINE config 4) or by interleaved 16-ROW BANDS (PARTITION_TILE,
+//                   crb_render_samples range, BASELINE config 4) or by interleaved 8-ROW BANDS (PARTITION_TILE,
 //                   BASELINE config 5); the sampler is keyed by global pixel and sample, so the union over ranks is
 //                   the single-GPU set of paths
 //   merge ("flush") snapshot of every rank's float4 accumulator (device-to-device on the render stream), then on a
@@ -38,10 +38,12 @@
 namespace crb
 {
     enum { PARTITION_SPP = 0, PARTITION_TILE = 1 };
-    // Height of the interleaved row bands of the tile partition. 16 rows: a 2160-row frame is 135 bands, i.e. 17 or 16 per GPU
-    // on 8 GPUs (row-count imbalance 0.7 %) and the 128-row period is short against the image content; with the 64 rows of
-    // SURVEY.md's example the same frame is 34 bands (5 or 4 per GPU) and config 5 scaled at 0.82 on 8 GPUs (profiles/r2q).
-    constexpr uint32_t TILE_BAND_ROWS = 16;
+    // Height of the interleaved row bands of the tile partition, and the owner order. Measured on one GPU by rendering the
+    // 8 ranks' shares of the 4K config-5 frame separately (tools/band_balance.py, profiles/r2_sweeps.md section 9), mean/max
+    // of the ranks' times = the strong-scaling efficiency the partition can reach: 64-row bands (SURVEY.md's example: 34 bands,
+    // 5 or 4 per GPU) 0.76, 16 rows 0.95, 16 rows serpentine 0.97, 8 rows serpentine 0.99. On the 8-GPU box config 5 scaled at
+    // 0.82 with 64-row and 0.955 with 16-row plain bands.
+    constexpr uint32_t TILE_BAND_ROWS = 8;
     constexpr uint32_t TILE_SERPENTINE = 1;    // owner order reversed in every other period of bands (render.cuh band_owner)
 
     // contiguous share [lo, hi) of `n` samples starting at `first` for `rank` of `world` (earlier ranks take the remainder)

@@ -26,7 +26,7 @@ def sample_range(rank: int, world: int, n_spp: int, first_sample: int = 0) -> Tu
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def row_bands(rank: int, world: int, height: int, band: int = 16):
+def row_bands(rank: int, world: int, height: int, band: int = 8):
     """Interleaved row bands [(y0, y1), ...] owned by `rank` (tile partition, BASELINE config 5)."""
     out = []
     for i, y0 in enumerate(range(0, height, band)):

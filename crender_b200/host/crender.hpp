@@ -210,7 +210,7 @@ namespace crb
             check(crb_render_create(scn->handle(), uint32_t(res_x), uint32_t(res_y), uint32_t(bounces), seed, 0, &_h));
         }
         // the same renderer over `ngpus` GPUs of this process (devices 0..ngpus-1): the library replicates the scene,
-        // splits every render(n) by sample index (CRB_PARTITION_SPP) or by interleaved 16-row bands (CRB_PARTITION_TILE) and
+        // splits every render(n) by sample index (CRB_PARTITION_SPP) or by interleaved 8-row bands (CRB_PARTITION_TILE) and
         // merges the accumulators; all getters return the merged image
         renderer(uint64_t res_x, uint64_t res_y, uint64_t bounces, scene *scn, uint32_t seed, int ngpus, int partition)
             : _scene(scn), _res_x(res_x), _res_y(res_y)

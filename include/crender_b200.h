@@ -281,7 +281,7 @@ int crb_render_post_process(crb_render *, const crb_post_settings *, float *out_
  *                            bands as grouped ncclBroadcasts (tile) + the resolve behind it, on a side stream.
  * partition: CRB_PARTITION_SPP — every crb_render_samples(first, n) range is split into contiguous shares, rank g
  * renders samples [first + g*n/N, ...) of every pixel (BASELINE config 4); CRB_PARTITION_TILE — rank g renders all n
- * samples of the interleaved 16-row bands g, g+N, ... (BASELINE config 5). The sampler is keyed by global pixel and sample index,
+ * samples of the interleaved 8-row bands g, g+N, ... (owner order reversed in every other period of N bands) (BASELINE config 5). The sampler is keyed by global pixel and sample index,
  * so the union over ranks is the single-GPU set of paths; tile merges are bit-identical to one GPU, spp merges differ
  * by float summation order only. crb_render_read / _read_async return the MERGED image (a flush is implied;
  * crb_render_flush starts one early). In rank mode reading an AOV buffer is a collective call and crb_render_stats
