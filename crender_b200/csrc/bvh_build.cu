@@ -508,8 +508,8 @@ namespace crb
         }
 
         // Models of at most 8 triangles (area-light quads, proxies of a small TLAS ...) are ONE node with one triangle per
-        // slot: written by a single thread, no sort, no hierarchy, no host round trips (a 65-model scene paid 65 x ~0.4 ms
-        // of launch and synchronisation latency for them). Same conservative quantisation as k_collapse; triangle j sits in
+        // slot: written by a single thread, no sort, no hierarchy, no host round trips (the full pipeline costs ~0.3 ms of
+        // launch and synchronisation latency whatever the size). Same conservative quantisation as k_collapse; triangle j sits in
         // slot nibble_order[j], so the triangle array is in the bit order of the occupancy word (bvh8.cuh).
         constexpr uint32_t TINY_BVH_MAX = 8;
         __global__ void k_tiny_bvh(const float *__restrict__ wv, uint32_t n, uint4 *__restrict__ nodes, float4 *__restrict__ tris)
