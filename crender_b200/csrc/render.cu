@@ -99,6 +99,28 @@ namespace crb
 #endif
         }
 
+        // Queue records are read once and written once per bounce: streaming loads / stores (evict-first) keep them from
+        // displacing BVH lines in the L1 / L2 the traversal lives on
+#ifndef CRB_STREAM_QUEUES
+#define CRB_STREAM_QUEUES 1
+#endif
+        __device__ __forceinline__ float4 ld_stream(const float4 *p)
+        {
+#if defined(CRB_EMU) || !CRB_STREAM_QUEUES
+            return *p;
+#else
+            return __ldcs(p);
+#endif
+        }
+        __device__ __forceinline__ void st_stream(float4 *p, float4 v)
+        {
+#if defined(CRB_EMU) || !CRB_STREAM_QUEUES
+            *p = v;
+#else
+            __stcs(p, v);
+#endif
+        }
+
         // Block-aggregated reservation of queue space in NQ queues at once: warps count with a ballot, add
         // into shared memory, and ONE thread per queue issues the global atomic for the whole block
         // (same-address global atomics serialise in L2; per-warp pushes of a full-frame wavefront are
@@ -262,7 +284,7 @@ namespace crb
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &slot, V3 &o, V3 &d, float &tmin, float &tmax) {
                 slot            = idx;    // the path records are in queue order: no indirection, coalesced loads
-                const float4 ro = ps.ray_o[idx], rd = ps.ray_d[idx];
+                const float4 ro = ld_stream(ps.ray_o + idx), rd = ld_stream(ps.ray_d + idx);
                 o               = v3(ro.x, ro.y, ro.z);
                 d               = normalize(v3(rd.x, rd.y, rd.z));    // model.cpp:107-112: the query direction is normalised
                 tmin = 0.00001f, tmax = inf_f();                      // model.cpp:21-22
@@ -270,7 +292,7 @@ namespace crb
             // retiring a ray is one 16-byte store; the material sort is a separate full-width pass
             // (k_classify) because only a few lanes of a warp retire at any refill point
             auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
-                if (valid) ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                if (valid) st_stream(ps.hit + slot, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
             };
             trace_persistent<COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_TRACE, n, ps.trace_chunk, false, source, sink, &tc);
             if (COUNT)
@@ -866,12 +888,12 @@ namespace crb
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &slot, V3 &o, V3 &d, float &tmin, float &tmax) {
                 slot            = idx;
-                const float4 ro = ps.ray_o[idx], rd = ps.ray_d[idx];
+                const float4 ro = ld_stream(ps.ray_o + idx), rd = ld_stream(ps.ray_d + idx);
                 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);    // as the reference holds it: every instance renormalises (model.cpp:110-112)
                 tmin = 0.00001f, tmax = inf_f();
             };
             auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
-                if (valid) ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                if (valid) st_stream(ps.hit + slot, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
             };
             trace_persistent_2l<COUNT, CRB_TRACE2_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_TRACE, n, false, source, sink, &tc);
             if (COUNT)
@@ -888,7 +910,7 @@ namespace crb
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
                 item            = idx;
-                const float4 so = ps.shadow[idx].o, sd = ps.shadow[idx].d;
+                const float4 so = ld_stream(&ps.shadow[idx].o), sd = ld_stream(&ps.shadow[idx].d);
                 o = v3(so.x, so.y, so.z), d = v3(sd.x, sd.y, sd.z);
                 tmin = 0.00001f, tmax = sd.w;    // inf for the sun, 0.999 * distance (world) for an area light
             };
@@ -919,7 +941,7 @@ namespace crb
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
                 item            = idx;
-                const float4 so = ps.shadow[idx].o, sd = ps.shadow[idx].d;
+                const float4 so = ld_stream(&ps.shadow[idx].o), sd = ld_stream(&ps.shadow[idx].d);
                 o               = v3(so.x, so.y, so.z);
                 d               = normalize(v3(sd.x, sd.y, sd.z));    // model.cpp:110-112
                 tmin = 0.00001f, tmax = sd.w;                         // inf for the sun, 0.999 * distance for an area light
