@@ -277,6 +277,7 @@ namespace crb
 #ifndef CRB_TRACE_BLOCK
 #define CRB_TRACE_BLOCK 128    // threads per CTA of the two single-level traversal kernels (at most 256: bvh8.cuh CRB_TP_SMEM)
 #endif
+        static_assert(CRB_TRACE_BLOCK <= 256 && CRB_TRACE_BLOCK % 32 == 0, "the trace loops keep per-lane state in shared arrays of 256 entries (bvh8.cuh)");
         template<bool COUNT, int STEPS>
         __global__ void __launch_bounds__(CRB_TRACE_BLOCK, CRB_TRACE_OCC) k_trace(DScene sc, PathState ps)
         {
