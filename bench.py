@@ -446,7 +446,14 @@ def trace_roofline(api, make_r, spp, steps, l2_bytes, g, traffic_key):
                          "bandwidth measured in this run; the kernel is bound by instruction issue at partial SIMD occupancy (issue_active, lanes_per_inst)"
                          % (bvh_bytes / 1e6, l2_bytes / 1e6))
     else:
-        out["regime"] = "the BVH (%.0f MB) does not fit the %.0f MB L2: node and triangle fetches miss to HBM, frac is a real HBM figure" % (bvh_bytes / 1e6, l2_bytes / 1e6)
+        tr = out["traffic"]
+        out["regime"] = ("the BVH (%.0f MB) does not fit the %.0f MB L2, but the committed ncu capture of this workload measures DRAM traffic of %s of the "
+                         "algorithmic bytes per launch (traffic / bytes_per_launch): the part of the tree a frame's rays touch is served by L1/L2 here too, so "
+                         "`frac` is not a bandwidth-saturation figure in this regime either; the kernel is bound by instruction issue at partial SIMD occupancy"
+                         % (bvh_bytes / 1e6, l2_bytes / 1e6, ("%.0f %%" % (100.0 * tr / bytes_per_launch)) if tr else "an unknown share"))
+        for k in ("issue_active", "lanes_per_inst", "warps_active"):
+            out[k] = committed_counters(traffic_key.replace("dram_bytes_per_launch", k))
+        out["counters_source"] = committed_counters(traffic_key.replace("dram_bytes_per_launch", "source"))
     return out
 
 
@@ -601,7 +608,10 @@ def partitioned_config(a, ctx, api, scenes, D, desc, w, h, bounces, total_spp, n
         def make_r(counters=False, timers=False):
             return api.renderer(w, h, bounces, g, seed=0, timers=timers, counters=counters, extended=extended)
 
-        out["roofline"] = trace_roofline(api, make_r, 16, 2, device_l2_bytes(api), g, "c4_k_trace_dram_bytes_per_launch")
+        # ncu figures: the flattened tree runs k_trace, the two-level default k_trace2 (separate committed captures)
+        out["roofline"] = trace_roofline(api, make_r, 16, 2, device_l2_bytes(api), g, ("c4_k_trace" if flatten else "c4tl_k_trace") + "_dram_bytes_per_launch")
+        if not flatten and any(m.instances is not None for m in desc.meshes):
+            out["roofline"]["kernel"] = "k_trace2 (closest-hit traversal, two-level)"
     return out
 
 

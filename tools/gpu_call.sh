@@ -17,8 +17,8 @@ for what in "$@"; do
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_ncu_l.log 2>&1; tail -2 $out/${tag}_ncu_l.log ;;
     ncu_trace) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace --launch-skip 8 --launch-count 8 -f -o $out/${tag}_prof_trace $B > $out/${tag}_ncu_t.log 2>&1; tail -2 $out/${tag}_ncu_t.log ;;
     ncu_shade) timeout 900 ncu --set full --clock-control none -k regex:'k_shadow|k_shade' --launch-skip 16 --launch-count 6 -f -o $out/${tag}_prof_shade $B > $out/${tag}_ncu_s.log 2>&1; tail -2 $out/${tag}_ncu_s.log ;;
-    ncu_c4flat) CRB_FLATTEN=1 timeout 900 ncu --set full --clock-control none -k regex:k_trace --launch-skip 8 --launch-count 4 -f -o $out/${tag}_prof_c4flat python tools/bench_configs.py c4 --spp 8 > $out/${tag}_ncu_c4.log 2>&1; tail -2 $out/${tag}_ncu_c4.log ;;
-    ncu_c4)  timeout 900 ncu --set full --clock-control none -k regex:'k_trace2|k_shadow2' --launch-skip 16 --launch-count 6 -f -o $out/${tag}_prof_c4 python tools/bench_configs.py c4 --spp 8 > $out/${tag}_ncu_c4tl.log 2>&1; tail -2 $out/${tag}_ncu_c4tl.log ;;
+    ncu_c4flat) CRB_FLATTEN=1 timeout 900 ncu --set full --clock-control none -k regex:k_trace --launch-skip 8 --launch-count 8 -f -o $out/${tag}_prof_c4flat python tools/bench_configs.py c4 --spp 16 > $out/${tag}_ncu_c4.log 2>&1; tail -2 $out/${tag}_ncu_c4.log ;;
+    ncu_c4)  timeout 900 ncu --set full --clock-control none -k regex:k_trace2 --launch-skip 8 --launch-count 8 -f -o $out/${tag}_prof_c4 python tools/bench_configs.py c4 --spp 16 > $out/${tag}_ncu_c4tl.log 2>&1; tail -2 $out/${tag}_ncu_c4tl.log ;;
     multi)   n=$(nvidia-smi -L | wc -l)
              ( time timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "multi or rank_mode or cpp_host_drives" ) > $out/${tag}_pytest_multi.log 2>&1; tail -8 $out/${tag}_pytest_multi.log
              for g in 1 2 4 8; do [ $g -le $n ] || continue

@@ -3,7 +3,7 @@
 bench.py quotes in its roofline object (per-launch DRAM traffic of the dominant kernel, issue-slot utilisation, lanes per
 instruction, warp occupancy), with their source named.
 
-    python tools/ncu_counters.py profiles/r2i_k_trace.json [profiles/r2i_c4flat_k_trace.json]
+    python tools/ncu_counters.py profiles/r2p_k_trace.json [profiles/r2ac_c4flat_k_trace.json [profiles/r2ad_c4tl_k_trace2.json]]
 """
 import json
 import os
@@ -37,7 +37,9 @@ if __name__ == "__main__":
     out = summarise(sys.argv[1], "k_trace")
     out["counters_source"] = out["k_trace_source"]
     if len(sys.argv) > 2:
-        out.update(summarise(sys.argv[2], "c4_k_trace"))
+        out.update(summarise(sys.argv[2], "c4_k_trace"))      # config 4 flattened: k_trace on the 1 GB tree
+    if len(sys.argv) > 3:
+        out.update(summarise(sys.argv[3], "c4tl_k_trace"))    # config 4 two-level (default): k_trace2
     dst = os.path.join(ROOT, "profiles", "r2_counters.json")
     json.dump(out, open(dst, "w"), indent=1)
     print(open(dst).read())
