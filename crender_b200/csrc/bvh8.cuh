@@ -360,7 +360,10 @@ namespace crb
     //   sink(valid, item, hit)               called by ALL lanes at a convergent point; valid lanes retire
     // `any` (any-hit vs closest-hit) is a RUN-TIME argument on purpose: both query kinds execute the same
     // compiled loop, so the bit-exact closest-hit parity tests cover the code any-hit queries run.
-    template<bool COUNT, int STEPS, typename Source, typename Sink>
+    // OFFSETS = true: every work item is a query against ITS OWN tree inside the concatenated arrays (a BLAS of a two-level
+    // scene): source(idx, item, o, d, tmin, tmax, node_off, tri_off) also returns the tree's node / triangle base (child and
+    // triangle indices inside a tree are relative to it); tmax < 0 marks an item with nothing to traverse.
+    template<bool COUNT, int STEPS, bool OFFSETS = false, typename Source, typename Sink>
     __device__ __forceinline__ void trace_persistent(const Bvh8 &bvh, uint32_t *cursor, uint32_t n, uint32_t chunk_max, bool any, Source source, Sink sink,
                                                      TravCounters *ctr)
     {
@@ -381,6 +384,7 @@ namespace crb
         unsigned       best_prim = INVALID_PRIM;
         uint2          group = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
         uint32_t       local_next = 0, local_end = 0;
+        uint32_t       node_off = 0;    // OFFSETS: base of the item's tree in bvh.nodes (its triangle base lives in r_dir.w)
         // reservation granularity: large enough to keep the cursor atomic rare, small enough that the last
         // ranges are spread over all warps of the grid
         const uint32_t total_warps = (gridDim.x * blockDim.x + CRB_WARP - 1) / CRB_WARP;
@@ -424,11 +428,15 @@ namespace crb
                         float    tmax;
                         uint32_t item;
                         V3       d;
-                        source(idx, item, o, d, tmin, tmax);
-                        r_dir  = make_float4(d.x, d.y, d.z, 0.0f);
+                        uint32_t tri_off = 0;
+                        if constexpr (OFFSETS)
+                            source(idx, item, o, d, tmin, tmax, node_off, tri_off);
+                        else
+                            source(idx, item, o, d, tmin, tmax);
+                        r_dir  = make_float4(d.x, d.y, d.z, __uint_as_float(tri_off));
                         r_win  = make_float4(0.0f, 0.0f, __uint_as_float(item), 0.0f);
                         best_t = tmax, best_prim = INVALID_PRIM;
-                        if (bvh.n_nodes == 0)
+                        if (bvh.n_nodes == 0 || (OFFSETS && tmax < 0.0f))
                         {
                             best_t   = __int_as_float(0x7f800000);
                             finished = true;
@@ -456,7 +464,7 @@ namespace crb
                     const unsigned node_index = pop_inner(group, oct4);
                     if (group.y) stack[sp++] = group;
 
-                    const uint4 *np = bvh.nodes + size_t(node_index) * 5;
+                    const uint4 *np = bvh.nodes + (OFFSETS ? size_t(node_off) + node_index : size_t(node_index)) * 5;
                     const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                     if (COUNT) ctr->nodes++;
                     node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, best_t, group, tgroup, occ);
@@ -492,9 +500,9 @@ namespace crb
                 {
                     if (pending)
                     {
-                        const float4 *tp = bvh.tris + size_t(pop_triangle(tgroup, occ)) * 3;
-                        const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
                         const float4  dq = r_dir;
+                        const float4 *tp = bvh.tris + (OFFSETS ? size_t(__float_as_uint(dq.w)) + pop_triangle(tgroup, occ) : size_t(pop_triangle(tgroup, occ))) * 3;
+                        const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
                         if (COUNT) ctr->tris++;
                         float t, u, v;
                         if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, v3(dq.x, dq.y, dq.z), tmin, best_t, t, u, v))

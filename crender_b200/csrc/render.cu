@@ -882,12 +882,14 @@ namespace crb
 #define CRB_TRACE2_OCC 4    // resident CTAs per SM of the two-level traversal kernels: 64 registers without spills since the TLAS-level ray
                             // lives in shared memory (bvh8.cuh CRB_2L_SMEM); measured on config 4: 3 CTAs 2086-2115, 4 CTAs 2331 Mrays/s
 #endif
-        template<bool COUNT>
+        // FB = true: the rays the instance wavefront could not take (more than IW_K candidate instances), by their queue
+        template<bool COUNT, bool FB = false>
         __global__ void __launch_bounds__(256, CRB_TRACE2_OCC) k_trace2(DScene sc, PathState ps)
         {
-            const uint32_t n = ps.counters[CTR_IN];
+            const uint32_t n = ps.counters[FB ? CTR_IW_FB : CTR_IN];
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &slot, V3 &o, V3 &d, float &tmin, float &tmax) {
+                if (FB) idx = ps.iw_fb[idx];
                 slot            = idx;
                 const float4 ro = ld_stream(ps.ray_o + idx), rd = ld_stream(ps.ray_d + idx);
                 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);    // as the reference holds it: every instance renormalises (model.cpp:110-112)
@@ -896,12 +898,283 @@ namespace crb
             auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
                 if (valid) st_stream(ps.hit + slot, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
             };
-            trace_persistent_2l<COUNT, CRB_TRACE2_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_TRACE, n, false, source, sink, &tc);
+            trace_persistent_2l<COUNT, CRB_TRACE2_STEPS, true>(sc.bvh2, ps.counters + (FB ? CTR_IW_FB_CUR : CTR_CUR_TRACE), n, false, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES, tc.nodes);
                 atomicAdd(ps.stats + ST_TRIS, tc.tris);
             }
+        }
+
+        // ------------------------------------------------------------------ two-level closest hit as a wavefront over instance visits
+        // The persistent two-level loop (k_trace2) pays for instance entries and exits inside its inner loop: ~290 + ~70
+        // instructions that some lane of a warp needs in almost every iteration, executed at 2 - 7 of 32 lanes (ncu source page:
+        // a third of the kernel's issue slots; 28 G node visits/s against 52 G in the single-level loop on the same geometry).
+        // Here every instance visit is a work item of its own:
+        //   k_iw_candidates  one thread per ray: walks the TLAS, keeps the (at most IW_K) instances whose world bounds the ray
+        //                    enters, sorted by entry distance, takes the ray into the nearest one's object space and emits
+        //                    the item; a ray with more candidates goes to the fallback queue (k_trace2 over that queue)
+        //   k_iw_trace       the SINGLE-LEVEL persistent loop over the items (object-space rays against their BLAS)
+        //   k_iw_next        one thread per item: re-measures the hit in world space and merges it into the ray's best
+        //                    (model.cpp:116-123), then emits the ray's next candidate unless its bounds start beyond the best
+        //                    hit, or writes the ray's final hit record
+        // for IW_K rounds. Same per-instance arithmetic, same candidate comparison (world distance, ties to the first
+        // (model, instance)) and the same conservative pruning as trace_persistent_2l: hits are bit-identical.
+        constexpr int IW_K = 8;
+#ifndef CRB_IW_DEFAULT
+#define CRB_IW_DEFAULT 0
+#endif
+
+        // entry into instance k (model.cpp:107-112 and the pruning bound of trace_persistent_2l): the object-space item
+        constexpr uint32_t IW_MORE = 0x80000000u;    // item flag: the ray has per-ray state (further candidates or a best hit so far)
+        __device__ __forceinline__ void iw_emit(const DScene &sc, const PathState &ps, int q, uint32_t at, uint32_t rec, uint32_t k, V3 wo, V3 wd, float best_key, bool more)
+        {
+            const float4 *ip = reinterpret_cast<const float4 *>(sc.bvh2.inst + k);
+            const float4  v0 = __ldg(ip), v1 = __ldg(ip + 1), v2 = __ldg(ip + 2);
+            const float   inv[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+            const V3      o = xf34(inv, wo, 1.0f);
+            const V3      d = normalize(xf34(inv, wd, 0.0f));
+            float         bound = best_key;
+            if (best_key < inf_f())
+            {
+                const float4 f0 = __ldg(ip + 3), f1 = __ldg(ip + 4), f2 = __ldg(ip + 5);
+                const float  fwd[12] = { f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w };
+                const V3     wdir = xf34(fwd, d, 0.0f);
+                bound             = (best_key / __fsqrt_rn(dot(wdir, wdir))) * 1.0001f;
+            }
+            ps.iw_item_o[q][at] = make_float4(o.x, o.y, o.z, __uint_as_float(rec));
+            ps.iw_item_d[q][at] = make_float4(d.x, d.y, d.z, bound);
+            ps.iw_item_k[q][at] = k | (more ? IW_MORE : 0u);
+        }
+
+        // entry distance of the ray into a world-space box, or a negative value if it misses (same slab arithmetic and
+        // slack as ray_box in bvh8.cuh; NaN - the origin on a face of a flat box - counts as an entry at distance 0)
+        __device__ __forceinline__ float iw_box_entry(V3 o, V3 idir, const float *lo, const float *hi, float tmin, float tmax)
+        {
+            const float ax = (lo[0] - o.x) * idir.x, bx = (hi[0] - o.x) * idir.x, ay = (lo[1] - o.y) * idir.y, by = (hi[1] - o.y) * idir.y;
+            const float az = (lo[2] - o.z) * idir.z, bz = (hi[2] - o.z) * idir.z;
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+            if (!(tn == tn) || !(tf == tf)) return 0.0f;
+            return tn <= tf * 1.00001f + 1e-30f ? tn : -1.0f;
+        }
+
+        // sorted insertion by (entry distance, instance index), fully unrolled so that the lists stay in registers
+        __device__ __forceinline__ void iw_insert(float (&ct)[IW_K], uint32_t (&ci)[IW_K], int &nc, float te, uint32_t k)
+        {
+#pragma unroll
+            for (int j = 0; j < IW_K; j++)
+            {
+                if (j < nc)
+                {
+                    if (ct[j] > te || (ct[j] == te && ci[j] > k))
+                    {
+                        const float    t0 = ct[j];
+                        const uint32_t k0 = ci[j];
+                        ct[j] = te, ci[j] = k, te = t0, k = k0;
+                    }
+                }
+                else if (j == nc)
+                    ct[j] = te, ci[j] = k;
+            }
+            nc++;
+        }
+        // one instance against the ray: its world bounds, then the list (false: the list is full, the ray needs the fallback)
+        __device__ __forceinline__ bool iw_consider(const DScene &sc, uint32_t k, V3 wo, V3 tidir, float (&ct)[IW_K], uint32_t (&ci)[IW_K], int &nc)
+        {
+            const float4 *ip = reinterpret_cast<const float4 *>(sc.bvh2.inst + k);
+            const float4  i6 = __ldg(ip + 6), i7 = __ldg(ip + 7);
+            const uint4   i8 = __ldg(reinterpret_cast<const uint4 *>(ip + 8));
+            const float   lo[3] = { i6.x, i6.y, i6.z }, hi[3] = { i7.x, i7.y, i7.z };
+            const float   te = iw_box_entry(wo, tidir, lo, hi, 0.0f, inf_f());
+            if (te < 0.0f || i8.z == 0u) return true;    // missed, or an instance of an empty model
+            if (nc == IW_K) return false;
+            iw_insert(ct, ci, nc, te, k);
+            return true;
+        }
+        constexpr uint32_t IW_BRUTE = 32;    // up to this many instances every ray tests every instance's bounds (uniform control flow) instead of walking the TLAS
+
+        template<bool COUNT>
+        __global__ void __launch_bounds__(256) k_iw_candidates(DScene sc, PathState ps)
+        {
+            const uint32_t n = ps.counters[CTR_IN];
+            unsigned long long nodes = 0;
+            // all threads of a block iterate together (the queue reservation is block-collective)
+            for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
+            {
+                const uint32_t rec = tile + threadIdx.x;
+                bool           emit = false, fallback = false;
+                V3             wo = v3(0, 0, 0), wd = v3(0, 0, 1);
+                uint32_t       first = 0;
+                bool           more  = false;
+                if (rec < n)
+                {
+                    const float4 ro = ld_stream(ps.ray_o + rec), rd = ld_stream(ps.ray_d + rec);
+                    wo = v3(ro.x, ro.y, ro.z), wd = v3(rd.x, rd.y, rd.z);
+                    const V3 td = normalize(wd), tidir = v3(safe_rcp(td.x), safe_rcp(td.y), safe_rcp(td.z));
+                    float    ct[IW_K];
+                    uint32_t ci[IW_K];
+                    int      nc = 0;
+                    for (int j = 0; j < IW_K; j++) ct[j] = -1.0f, ci[j] = 0u;
+                    if (sc.bvh2.n_inst <= IW_BRUTE)
+                    {
+                        for (uint32_t k = 0; k < sc.bvh2.n_inst; k++)
+                            if (!iw_consider(sc, k, wo, tidir, ct, ci, nc)) fallback = true;
+                    }
+                    else if (sc.bvh2.tlas.n_nodes != 0)
+                    {
+                        // the TLAS is a few nodes deep: a plain per-thread walk, every leaf proxy = one instance
+                        const unsigned oct4 = make_oct4(td);
+                        uint2          stack[BVH8_STACK];
+                        int            sp = 0;
+                        uint2          group = make_uint2(0u, 0x80000000u), tgroup;
+                        unsigned       occ;
+                        for (;;)
+                        {
+                            const unsigned node_index = pop_inner(group, oct4);
+                            if (group.y) stack[sp++] = group;
+                            const uint4 *np = sc.bvh2.tlas.nodes + size_t(node_index) * 5;
+                            const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                            if (COUNT) nodes++;
+                            node_visit(n0, n1, n2, n3, n4, wo, tidir, oct4, 0.0f, inf_f(), group, tgroup, occ);
+                            while (tgroup.y)
+                            {
+                                const uint32_t k = __float_as_uint(__ldg(sc.bvh2.tlas.tris + size_t(pop_triangle(tgroup, occ)) * 3).w);
+                                if (!iw_consider(sc, k, wo, tidir, ct, ci, nc)) fallback = true;
+                            }
+                            if (group.y == 0u)
+                            {
+                                if (sp == 0) break;
+                                group = stack[--sp];
+                            }
+                        }
+                    }
+                    if (!fallback)
+                    {
+                        static_assert(IW_K == 8, "the candidate lists are stored as two 16-byte vectors each");
+                        float4 *pt = reinterpret_cast<float4 *>(ps.iw_cand_t + size_t(rec) * IW_K);
+                        uint4  *pi = reinterpret_cast<uint4 *>(ps.iw_cand_i + size_t(rec) * IW_K);
+                        // a ray with ONE candidate needs no per-ray state: its item's hit is its hit (k_iw_next); the others keep
+                        // their list, and round 0 of k_iw_next initialises (best hit, its world distance, its instance, next candidate)
+                        if (nc > 1)
+                        {
+                            pt[0] = make_float4(ct[0], ct[1], ct[2], ct[3]), pt[1] = make_float4(ct[4], ct[5], ct[6], ct[7]);
+                            pi[0] = make_uint4(ci[0], ci[1], ci[2], ci[3]), pi[1] = make_uint4(ci[4], ci[5], ci[6], ci[7]);
+                            more = true;
+                        }
+                        if (nc)
+                            emit = true, first = ci[0];
+                        else
+                            st_stream(ps.hit + rec, make_float4(inf_f(), 0.f, 0.f, __uint_as_float(INVALID_PRIM)));
+                    }
+                }
+                const bool pred[2] = { emit, fallback };
+                const int  cidx[2] = { CTR_IW_ITEMS, CTR_IW_FB };
+                uint32_t   at[2];
+                block_reserve<2>(pred, ps.counters, cidx, at);
+                if (emit) iw_emit(sc, ps, 0, at[0], rec, first, wo, wd, inf_f(), more);
+                if (fallback) ps.iw_fb[at[1]] = rec;
+            }
+            if (COUNT) atomicAdd(ps.stats + ST_NODES, nodes);
+        }
+
+        template<bool COUNT>
+        __global__ void __launch_bounds__(CRB_TRACE_BLOCK, CRB_TRACE_OCC) k_iw_trace(DScene sc, PathState ps, int q)
+        {
+            const uint32_t n = ps.counters[CTR_IW_ITEMS + q];
+            TravCounters   tc;
+            const Bvh8     all { sc.bvh2.nodes, sc.bvh2.tris, 1u, 1u };    // every BLAS, concatenated; the item names its own
+            auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax, uint32_t &node_off, uint32_t &tri_off) {
+                item            = idx;
+                const float4 io = ld_stream(ps.iw_item_o[q] + idx), id = ld_stream(ps.iw_item_d[q] + idx);
+                const uint4  i8 = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const float4 *>(sc.bvh2.inst + (ps.iw_item_k[q][idx] & ~IW_MORE)) + 8));
+                o = v3(io.x, io.y, io.z), d = v3(id.x, id.y, id.z);
+                tmin = 0.00001f, tmax = id.w;    // model.cpp:21; the pruning bound of the entry
+                node_off = i8.x, tri_off = i8.y;
+            };
+            auto sink = [&](bool valid, uint32_t item, const Hit &h) {
+                if (valid) st_stream(ps.iw_item_hit + item, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
+            };
+            trace_persistent<COUNT, TRACE_STEPS, true>(all, ps.counters + CTR_IW_CUR, n, ps.trace_chunk, false, source, sink, &tc);
+            if (COUNT)
+            {
+                atomicAdd(ps.stats + ST_NODES, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS, tc.tris);
+            }
+        }
+
+        __global__ void __launch_bounds__(256) k_iw_next(DScene sc, PathState ps, int q, int round)
+        {
+            const uint32_t n = ps.counters[CTR_IW_ITEMS + q];
+            for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
+            {
+                const uint32_t idx  = tile + threadIdx.x;
+                bool           emit = false;
+                uint32_t       rec = 0, next_k = 0;
+                V3             wo = v3(0, 0, 0), wd = v3(0, 0, 1);
+                float          best_key = inf_f();
+                if (idx < n)
+                {
+                    const float4   io = ld_stream(ps.iw_item_o[q] + idx), h = ld_stream(ps.iw_item_hit + idx);
+                    const uint32_t kf = ps.iw_item_k[q][idx], cur = kf & ~IW_MORE;
+                    rec               = __float_as_uint(io.w);
+                    const float4 *ip  = reinterpret_cast<const float4 *>(sc.bvh2.inst + cur);
+                    if (!(kf & IW_MORE))
+                    {
+                        // the ray's only candidate: no comparison, no re-measuring — its hit is the hit
+                        const uint32_t prim = __float_as_uint(h.w);
+                        st_stream(ps.hit + rec, prim == INVALID_PRIM ? make_float4(inf_f(), 0.f, 0.f, h.w) : make_float4(h.x, h.y, h.z, __uint_as_float(__float_as_uint(__ldg(ip + 7).w) + prim)));
+                    }
+                    else
+                    {
+                    const float4 id = ld_stream(ps.iw_item_d[q] + idx);
+                    const float4 ro = ps.ray_o[rec], rd = ps.ray_d[rec];
+                    wo = v3(ro.x, ro.y, ro.z), wd = v3(rd.x, rd.y, rd.z);
+                    float4   best = make_float4(inf_f(), 0.f, 0.f, __uint_as_float(INVALID_PRIM)), meta = make_float4(inf_f(), __uint_as_float(0xffffffffu), __uint_as_float(1u), 0.f);
+                    if (round != 0) best = ps.iw_best[rec], meta = ps.iw_meta[rec];
+                    uint32_t best_k = __float_as_uint(meta.y), nxt = __float_as_uint(meta.z);
+                    best_key        = meta.x;
+                    if (__float_as_uint(h.w) != INVALID_PRIM)
+                    {
+                        // leave the instance: model.cpp:116-123 (map the point back, re-measure, keep the nearest)
+                        const float4  f0 = __ldg(ip + 3), f1 = __ldg(ip + 4), f2 = __ldg(ip + 5);
+                        const float   fwd[12] = { f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w };
+                        const V3      o = v3(io.x, io.y, io.z), d = v3(id.x, id.y, id.z);
+                        const float   key = length(xf34(fwd, o + d * h.x, 1.0f) - wo);    // glm::distance(point, ray.origin)
+                        if (key < best_key || (key == best_key && cur < best_k))
+                        {
+                            best     = make_float4(h.x, h.y, h.z, __uint_as_float(__float_as_uint(__ldg(ip + 7).w) + __float_as_uint(h.w)));
+                            best_key = key, best_k = cur;
+                        }
+                    }
+                    // the next candidate, unless its bounds begin beyond the best hit (the candidates are sorted by entry distance)
+                    if (nxt < uint32_t(IW_K))
+                    {
+                        const float te = ps.iw_cand_t[size_t(rec) * IW_K + nxt];
+                        if (te >= 0.0f && te <= best_key * 1.00001f + 1e-30f) emit = true, next_k = ps.iw_cand_i[size_t(rec) * IW_K + nxt], nxt++;
+                    }
+                    if (emit)
+                    {
+                        ps.iw_best[rec] = best;
+                        ps.iw_meta[rec] = make_float4(best_key, __uint_as_float(best_k), __uint_as_float(nxt), 0.f);
+                    }
+                    else
+                        st_stream(ps.hit + rec, __float_as_uint(best.w) == INVALID_PRIM ? make_float4(inf_f(), 0.f, 0.f, best.w) : best);
+                    }
+                }
+                const bool pred[1] = { emit };
+                const int  cidx[1] = { CTR_IW_ITEMS + (q ^ 1) };
+                uint32_t   at[1];
+                block_reserve<1>(pred, ps.counters, cidx, at);
+                if (emit) iw_emit(sc, ps, q ^ 1, at[0], rec, next_k, wo, wd, best_key, true);
+            }
+        }
+
+        // one thread: the consumed item queue becomes the next round's target, the cursor of the item loop is reset
+        __global__ void k_iw_roll(PathState ps, int q)
+        {
+            ps.counters[CTR_IW_ITEMS + q] = 0;
+            ps.counters[CTR_IW_CUR]       = 0;
         }
 
         template<bool COUNT>
@@ -1033,6 +1306,7 @@ namespace crb
             c[CTR_NEXT] = 0, c[CTR_SHADOW] = 0;
             c[CTR_CLASS0] = c[CTR_CLASS0 + 1] = c[CTR_CLASS0 + 2] = c[CTR_CLASS0 + 3] = 0;
             c[CTR_CUR_TRACE] = c[CTR_CUR_SHADE] = c[CTR_CUR_SHADOW] = 0;
+            c[CTR_IW_ITEMS] = c[CTR_IW_ITEMS + 1] = c[CTR_IW_CUR] = c[CTR_IW_FB] = c[CTR_IW_FB_CUR] = 0;
         }
 
         // ------------------------------------------------------------------ K9 accumulate + resolve
@@ -1187,6 +1461,16 @@ namespace crb
         capacity = n;
     }
 
+    // state of the instance wavefront (two-level scenes only): 188 B per path on top of the 200
+    void Render::ensure_iw(size_t n)
+    {
+        if (n <= iw_capacity) return;
+        sync();
+        iw_cand_t.alloc(n * 8), iw_cand_i.alloc(n * 8), iw_best.alloc(n), iw_meta.alloc(n), iw_item_hit.alloc(n), iw_fb.alloc(n);
+        for (int q = 0; q < 2; q++) iw_item_o[q].alloc(n), iw_item_d[q].alloc(n), iw_item_k[q].alloc(n);
+        iw_capacity = n;
+    }
+
     void Render::collect_time(bool wait)
     {
 #ifndef CRB_EMU
@@ -1277,7 +1561,7 @@ namespace crb
             // never plan for more than a quarter of the free device memory (200 B of state per path)
             const auto t_a = now();
             if (capacity == 0)
-                if (const size_t avail = dev_available_bytes()) mem_path_cap = std::max<size_t>(size_t(1) << 20, avail / 4 / 200);
+                if (const size_t avail = dev_available_bytes()) mem_path_cap = std::max<size_t>(size_t(1) << 20, avail / 4 / (dscene.two_level ? 400 : 200));    // + 188 B for the instance wavefront
             if (mem_path_cap) tpaths = std::min(tpaths, mem_path_cap);
             ms_meminfo = ms_since(t_a);
         }
@@ -1296,6 +1580,13 @@ namespace crb
         ps.q_in = q_in.p, ps.q_next = q_next.p;
         for (int c = 0; c < 4; c++) ps.q_class[c] = q_class[c].p;
         ps.shadow = shadow.p, ps.counters = counters.p, ps.stats = dstats.p;
+        // closest hit of two-level scenes as a wavefront over instance visits (k_iw_*): CRB_INSTANCE_WAVEFRONT=0 keeps the
+        // persistent two-level loop for everything
+        static const int iw_env = getenv("CRB_INSTANCE_WAVEFRONT") ? atoi(getenv("CRB_INSTANCE_WAVEFRONT")) : CRB_IW_DEFAULT;
+        const bool iw = dscene.two_level && iw_env != 0;
+        if (iw) ensure_iw(capacity);
+        ps.iw_cand_t = iw_cand_t.p, ps.iw_cand_i = iw_cand_i.p, ps.iw_best = iw_best.p, ps.iw_meta = iw_meta.p, ps.iw_item_hit = iw_item_hit.p, ps.iw_fb = iw_fb.p;
+        for (int q = 0; q < 2; q++) ps.iw_item_o[q] = iw_item_o[q].p, ps.iw_item_d[q] = iw_item_d[q].p, ps.iw_item_k[q] = iw_item_k[q].p;
         static const uint32_t trace_chunk = getenv("CRB_TRACE_CHUNK") ? uint32_t(atoi(getenv("CRB_TRACE_CHUNK"))) : 0u;    // tuning knob
         ps.trace_chunk = trace_chunk;
         // material sort before shading: implemented (k_classify + per-class queues) but OFF by default — the
@@ -1345,7 +1636,31 @@ namespace crb
             {
                 rp.bounce = i;
                 tick(CRB_K_TRACE);
-                if (dscene.two_level)
+                if (dscene.two_level && iw)
+                {
+                    // closest hit as a wavefront over instance visits: candidates, then IW_K rounds of (single-level loop over the
+                    // items, merge + next candidate), then the general loop over the rays with more than IW_K candidates
+                    if (count)
+                        CRB_LAUNCH((k_iw_candidates<true>), pgrid, pblock, st, dscene, ps);
+                    else
+                        CRB_LAUNCH((k_iw_candidates<false>), pgrid, pblock, st, dscene, ps);
+                    for (int round = 0; round < IW_K; round++)
+                    {
+                        const int q = round & 1;
+                        if (count)
+                            CRB_LAUNCH((k_iw_trace<true>), tgrid, tblock, st, dscene, ps, q);
+                        else
+                            CRB_LAUNCH((k_iw_trace<false>), tgrid, tblock, st, dscene, ps, q);
+                        CRB_LAUNCH(k_iw_next, pgrid, pblock, st, dscene, ps, q, round);
+                        CRB_LAUNCH(k_iw_roll, 1, 1, st, ps, q);
+                    }
+                    if (count)
+                        CRB_LAUNCH((k_trace2<true, true>), t2grid, pblock, st, dscene, ps);
+                    else
+                        CRB_LAUNCH((k_trace2<false, true>), t2grid, pblock, st, dscene, ps);
+                    launches += 1 + 3 * IW_K;
+                }
+                else if (dscene.two_level)
                 {
                     if (count)
                         CRB_LAUNCH((k_trace2<true>), t2grid, pblock, st, dscene, ps);

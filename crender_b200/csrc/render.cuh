@@ -28,12 +28,24 @@ namespace crb
         uint32_t *q_next;       // path slots of the next bounce's records
         uint32_t *q_class[4];   // after trace: record indices by class: 0 miss, 1 metal, 2 smooth, 3 glass (material sort)
         ShadowRay *shadow;
+        // instance wavefront (two-level scenes, render.cu k_iw_*): per ray [queue position] the candidate instances sorted by
+        // entry distance (8 each), the best hit so far (t, u, v, flat prim) and (its world distance, its instance, the next
+        // candidate); two item queues (object-space origin + ray, direction + pruning bound, instance), the items' hits, the
+        // fallback queue
+        float    *iw_cand_t;
+        uint32_t *iw_cand_i;
+        float4   *iw_best, *iw_meta;
+        float4   *iw_item_o[2], *iw_item_d[2];
+        uint32_t *iw_item_k[2];
+        float4   *iw_item_hit;
+        uint32_t *iw_fb;
         uint32_t  *counters;    // see CTR_* below
         unsigned long long *stats;    // see ST_* below
         uint32_t  trace_chunk;        // work-reservation granularity of the persistent trace loop (0 = exact)
         int       sorted;             // 1: k_classify sorts paths by shade class before k_shade; 0: shade in queue order
     };
-    enum { CTR_IN = 0, CTR_CLASS0 = 1, CTR_NEXT = 5, CTR_SHADOW = 6, CTR_CUR_TRACE = 7, CTR_CUR_SHADE = 8, CTR_CUR_SHADOW = 9, CTR_COUNT = 16 };
+    enum { CTR_IN = 0, CTR_CLASS0 = 1, CTR_NEXT = 5, CTR_SHADOW = 6, CTR_CUR_TRACE = 7, CTR_CUR_SHADE = 8, CTR_CUR_SHADOW = 9,
+           CTR_IW_ITEMS = 10 /* and 11: the two item queues */, CTR_IW_CUR = 12, CTR_IW_FB = 13, CTR_IW_FB_CUR = 14, CTR_COUNT = 16 };
     enum { ST_CLOSEST = 0, ST_SHADOW = 1, ST_RANOUT = 2, ST_NODES = 3, ST_TRIS = 4, ST_NODES_SHADOW = 5, ST_TRIS_SHADOW = 6, ST_COUNT = 8 };
 
     // display = pow(clamp(sum / n, 0, 1), 1/2.2), alpha 1 (renderer.cpp:371-383); shared by the single-GPU accumulate
@@ -88,6 +100,10 @@ namespace crb
         // path state
         size_t              capacity = 0;
         DBuf<float4>        ray_o, ray_d, thr, rad, hit, ray_o2, ray_d2, thr2;
+        size_t              iw_capacity = 0;
+        DBuf<float>         iw_cand_t;
+        DBuf<uint32_t>      iw_cand_i, iw_item_k[2], iw_fb;
+        DBuf<float4>        iw_best, iw_meta, iw_item_o[2], iw_item_d[2], iw_item_hit;
         DBuf<uint32_t>      q_in, q_next, q_class[4];
         DBuf<ShadowRay>     shadow;
         DBuf<uint32_t>      counters;
@@ -156,6 +172,7 @@ namespace crb
     private:
         void alloc_images();
         void ensure_paths(size_t n);
+        void ensure_iw(size_t n);
         void collect_time(bool wait = true);
         const float4 *buffer_of(int kind) const;
     };

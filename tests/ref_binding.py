@@ -68,7 +68,7 @@ def scene_bytes(desc, w, h, bounces, spp, threads=1) -> bytes:
     return b"".join(out)
 
 
-def render(desc, w, h, bounces, spp, binary=None, timeout=15, retries=8, threads=1) -> dict:
+def render(desc, w, h, bounces, spp, binary=None, timeout=5, retries=40, threads=1) -> dict:
     """Runs the compiled reference on `desc` with a one-thread pool. Returns raw (h,w,3) sums, the four RGBA images,
     and draws_before (randf() draws of the empty-scene passes the renderer completed before the scene was handed over)."""
     binary = binary or build()
@@ -77,7 +77,9 @@ def render(desc, w, h, bounces, spp, binary=None, timeout=15, retries=8, threads
         open(src, "wb").write(scene_bytes(desc, w, h, bounces, spp, threads))
         for attempt in range(retries):
             # (the reference's pause()/thread-pool hand-shakes wait on condition variables without predicates,
-            # renderer.cpp:172-183, thread_pool.cpp:12-13,55-56: a lost wake-up hangs it — time out and retry)
+            # renderer.cpp:172-183, thread_pool.cpp:12-13,55-56: a lost wake-up hangs it — time out and retry. Measured: 0 - 50 %
+            # of the attempts hang depending on the scene while a good run of these small cases takes 0.1 - 0.3 s, hence a
+            # short time-out and many retries)
             try:
                 r = subprocess.run([binary, "render", src, dst], capture_output=True, text=True, timeout=timeout)
             except subprocess.TimeoutExpired:
