@@ -922,7 +922,7 @@ namespace crb
         // (model, instance)) and the same conservative pruning as trace_persistent_2l: hits are bit-identical.
         constexpr int IW_K = 8;
 #ifndef CRB_IW_DEFAULT
-#define CRB_IW_DEFAULT 0
+#define CRB_IW_DEFAULT 1    // measured on config 4 (profiles/r2_sweeps.md section 13): 2315 -> 2603 Mrays/s, k_trace2 2104 -> 2489 closest-hit Mrays/s
 #endif
 
         // entry into instance k (model.cpp:107-112 and the pruning bound of trace_persistent_2l): the object-space item
@@ -1306,6 +1306,9 @@ namespace crb
             c[CTR_NEXT] = 0, c[CTR_SHADOW] = 0;
             c[CTR_CLASS0] = c[CTR_CLASS0 + 1] = c[CTR_CLASS0 + 2] = c[CTR_CLASS0 + 3] = 0;
             c[CTR_CUR_TRACE] = c[CTR_CUR_SHADE] = c[CTR_CUR_SHADOW] = 0;
+#ifdef CRB_EMU
+            if (getenv("CRB_IW_DEBUG")) fprintf(stderr, "iw: %u rays of this bounce went to the fallback queue\n", unsigned(c[CTR_IW_FB]));    // kernel-logic harness only
+#endif
             c[CTR_IW_ITEMS] = c[CTR_IW_ITEMS + 1] = c[CTR_IW_CUR] = c[CTR_IW_FB] = c[CTR_IW_FB_CUR] = 0;
         }
 

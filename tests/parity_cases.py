@@ -806,3 +806,49 @@ def check_tiny_models(oracle, lib_path):
             for f in ("prim", "model", "inst", "t", "u", "v"):
                 np.testing.assert_array_equal(hg[f], ho[f], err_msg=f"n={n} {f}")
             np.testing.assert_array_equal(g.occluded(rays).astype(bool), hg["prim"] != common.MISS)
+
+
+IW_HASH_SNIPPET = r"""
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, {root!r})
+from crender_b200 import api, scenes
+from crender_b200.api import material
+rs = np.random.RandomState(4)
+box = scenes._box((0, 0, 0), (0.35, 0.35, 0.35), 15.0).astype(np.float32)
+ground = scenes._quad((-30, -0.5, -30), (-30, -0.5, 30), (30, -0.5, 30), (30, -0.5, -30)).astype(np.float32)
+def soup(n, spread):
+    inst = np.stack([scenes.compose(scenes.translation(rs.uniform(-spread, spread), rs.uniform(0, 2), rs.uniform(-spread, spread)), scenes.rotation_y(rs.uniform(0, 360))) for _ in range(n)]).astype(np.float32)
+    return scenes.SceneDesc("soup", [scenes.MeshDesc(ground, np.zeros(2, np.uint32), [material()], name="ground"),
+                                     scenes.MeshDesc(box, np.zeros(12, np.uint32), [material()], instances=inst, name="box")],
+                            api.camera(position=(0.0, 3.0, -12.0), fov=60.0, rotation=(0.0, 12.0, 0.0)))
+cases = dict(terrain=scenes.terrain_city(24, 2, n_buildings=12),     # 8 instances of two models: every ray tests every instance's bounds
+             sparse=soup(60, 12.0),                                   # more than 32 instances: the candidates come from a TLAS walk
+             crowded=soup(200, 1.2))                                  # rays with more than 8 candidate instances: the fallback queue
+for name, desc in cases.items():
+    g = api.scene(lib_path={lib!r}); scenes.load(desc, g); g.commit()
+    r = api.renderer(96, 54, 5, g, seed=9); r.render(4)
+    print("HASH", name, hashlib.sha256(r.raw_sum().tobytes()).hexdigest(), hashlib.sha256(r.current_depths().tobytes()).hexdigest(), r.current_stats().kernel_launches)
+"""
+
+
+def check_instance_wavefront_equals_loop(lib_path):
+    """Two-level scenes trace their closest hits as a wavefront over instance visits (k_iw_*) or — CRB_INSTANCE_WAVEFRONT=0,
+    read once per process — in the persistent two-level loop: both must give the same bits, for few instances (every ray
+    tests every instance), many (TLAS walk) and crowded ones (rays with more candidates than the lists hold: fallback)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = IW_HASH_SNIPPET.format(root=root, lib=lib_path)
+    res = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, CRB_INSTANCE_WAVEFRONT=mode)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[mode] = {l.split()[1]: l.split()[2:] for l in out.stdout.splitlines() if l.startswith("HASH")}
+    assert set(res["0"]) == {"terrain", "sparse", "crowded"}
+    for name in res["0"]:
+        assert res["0"][name][:2] == res["1"][name][:2], name
+        assert int(res["1"][name][2]) > int(res["0"][name][2]), "the wavefront path did not run"

@@ -87,3 +87,7 @@ def test_two_level_edge_cases(oracle, emu_lib):
 
 def test_tiny_models(oracle, emu_lib):
     pc.check_tiny_models(oracle, emu_lib)
+
+
+def test_instance_wavefront_equals_loop(emu_lib):
+    pc.check_instance_wavefront_equals_loop(emu_lib)

@@ -220,6 +220,10 @@ def test_tiny_models(oracle, product_lib):
     pc.check_tiny_models(oracle, product_lib)
 
 
+def test_instance_wavefront_equals_loop(product_lib):
+    pc.check_instance_wavefront_equals_loop(product_lib)
+
+
 def test_against_golden_fixtures(product_lib):
     """The CUDA path against the committed fixtures (no oracle at run time for this test)."""
     import os
