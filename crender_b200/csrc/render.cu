@@ -994,22 +994,10 @@ namespace crb
         }
         constexpr uint32_t IW_BRUTE = 32;    // up to this many instances every ray tests every instance's bounds (uniform control flow) instead of walking the TLAS
 
-        // the sun is visible from a shadow ray's origin: connect (renderer.cpp:348-353)
-        __device__ __forceinline__ void iw_connect(const PathState &ps, uint32_t rec)
-        {
-            const uint32_t slot = __float_as_uint(ps.shadow[rec].o.w);
-            const float4   c    = ps.shadow[rec].c;
-            const float4   r4   = ps.rad[slot];
-            const V3       r    = v3(r4.x, r4.y, r4.z) + v3(c.x, c.y, c.z);
-            ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
-        }
-
-        // SHADOW: the rays are the bounce's UNBOUNDED shadow rays (the sun): any triangle of any candidate instance occludes,
-        // so the items are any-hit queries, nothing is re-measured or compared, and a ray whose candidates all miss connects
-        template<bool COUNT, bool SHADOW>
+        template<bool COUNT>
         __global__ void __launch_bounds__(256) k_iw_candidates(DScene sc, PathState ps)
         {
-            const uint32_t n = ps.counters[SHADOW ? CTR_SHADOW : CTR_IN];
+            const uint32_t n = ps.counters[CTR_IN];
             unsigned long long nodes = 0;
             // all threads of a block iterate together (the queue reservation is block-collective)
             for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
@@ -1021,7 +1009,7 @@ namespace crb
                 bool           more  = false;
                 if (rec < n)
                 {
-                    const float4 ro = SHADOW ? ld_stream(&ps.shadow[rec].o) : ld_stream(ps.ray_o + rec), rd = SHADOW ? ld_stream(&ps.shadow[rec].d) : ld_stream(ps.ray_d + rec);
+                    const float4 ro = ld_stream(ps.ray_o + rec), rd = ld_stream(ps.ray_d + rec);
                     wo = v3(ro.x, ro.y, ro.z), wd = v3(rd.x, rd.y, rd.z);
                     const V3 td = normalize(wd), tidir = v3(safe_rcp(td.x), safe_rcp(td.y), safe_rcp(td.z));
                     float    ct[IW_K];
@@ -1076,8 +1064,6 @@ namespace crb
                         }
                         if (nc)
                             emit = true, first = ci[0];
-                        else if (SHADOW)
-                            iw_connect(ps, rec);
                         else
                             st_stream(ps.hit + rec, make_float4(inf_f(), 0.f, 0.f, __uint_as_float(INVALID_PRIM)));
                     }
@@ -1089,11 +1075,11 @@ namespace crb
                 if (emit) iw_emit(sc, ps, 0, at[0], rec, first, wo, wd, inf_f(), more);
                 if (fallback) ps.iw_fb[at[1]] = rec;
             }
-            if (COUNT) atomicAdd(ps.stats + (SHADOW ? ST_NODES_SHADOW : ST_NODES), nodes);
+            if (COUNT) atomicAdd(ps.stats + ST_NODES, nodes);
         }
 
         template<bool COUNT>
-        __global__ void __launch_bounds__(CRB_TRACE_BLOCK, CRB_TRACE_OCC) k_iw_trace(DScene sc, PathState ps, int q, int any)
+        __global__ void __launch_bounds__(CRB_TRACE_BLOCK, CRB_TRACE_OCC) k_iw_trace(DScene sc, PathState ps, int q)
         {
             const uint32_t n = ps.counters[CTR_IW_ITEMS + q];
             TravCounters   tc;
@@ -1109,52 +1095,11 @@ namespace crb
             auto sink = [&](bool valid, uint32_t item, const Hit &h) {
                 if (valid) st_stream(ps.iw_item_hit + item, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
             };
-            trace_persistent<COUNT, TRACE_STEPS, true>(all, ps.counters + CTR_IW_CUR, n, ps.trace_chunk, any != 0, source, sink, &tc);
+            trace_persistent<COUNT, TRACE_STEPS, true>(all, ps.counters + CTR_IW_CUR, n, ps.trace_chunk, false, source, sink, &tc);
             if (COUNT)
             {
-                atomicAdd(ps.stats + (any ? ST_NODES_SHADOW : ST_NODES), tc.nodes);
-                atomicAdd(ps.stats + (any ? ST_TRIS_SHADOW : ST_TRIS), tc.tris);
-            }
-        }
-
-        // shadow rays: an item that hit anything ends its ray (occluded); otherwise the ray's next candidate, or the connection
-        __global__ void __launch_bounds__(256) k_iw_next_shadow(DScene sc, PathState ps, int q, int round)
-        {
-            const uint32_t n = ps.counters[CTR_IW_ITEMS + q];
-            for (uint32_t tile = blockIdx.x * blockDim.x; tile < n; tile += gridDim.x * blockDim.x)
-            {
-                const uint32_t idx  = tile + threadIdx.x;
-                bool           emit = false, more = false;
-                uint32_t       rec = 0, next_k = 0;
-                if (idx < n)
-                {
-                    const uint32_t kf = ps.iw_item_k[q][idx];
-                    rec               = __float_as_uint(ld_stream(ps.iw_item_o[q] + idx).w);
-                    if (__float_as_uint(ld_stream(ps.iw_item_hit + idx).w) == INVALID_PRIM)
-                    {
-                        if (kf & IW_MORE)
-                        {
-                            const uint32_t nxt = round == 0 ? 1u : __float_as_uint(ps.iw_meta[rec].z);
-                            const float    te  = nxt < uint32_t(IW_K) ? ps.iw_cand_t[size_t(rec) * IW_K + nxt] : -1.0f;
-                            if (te >= 0.0f)
-                            {
-                                emit = true, next_k = ps.iw_cand_i[size_t(rec) * IW_K + nxt];
-                                more = nxt + 1 < uint32_t(IW_K) && ps.iw_cand_t[size_t(rec) * IW_K + nxt + 1] >= 0.0f;
-                                if (more) ps.iw_meta[rec] = make_float4(0.f, 0.f, __uint_as_float(nxt + 1), 0.f);
-                            }
-                        }
-                        if (!emit) iw_connect(ps, rec);
-                    }
-                }
-                const bool pred[1] = { emit };
-                const int  cidx[1] = { CTR_IW_ITEMS + (q ^ 1) };
-                uint32_t   at[1];
-                block_reserve<1>(pred, ps.counters, cidx, at);
-                if (emit)
-                {
-                    const float4 so = ps.shadow[rec].o, sd = ps.shadow[rec].d;
-                    iw_emit(sc, ps, q ^ 1, at[0], rec, next_k, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), inf_f(), more);
-                }
+                atomicAdd(ps.stats + ST_NODES, tc.nodes);
+                atomicAdd(ps.stats + ST_TRIS, tc.tris);
             }
         }
 
@@ -1226,20 +1171,18 @@ namespace crb
         }
 
         // one thread: the consumed item queue becomes the next round's target, the cursor of the item loop is reset
-        __global__ void k_iw_roll(PathState ps, int q, int reset_fallback)
+        __global__ void k_iw_roll(PathState ps, int q)
         {
             ps.counters[CTR_IW_ITEMS + q] = 0;
             ps.counters[CTR_IW_CUR]       = 0;
-            if (reset_fallback) ps.counters[CTR_IW_FB] = ps.counters[CTR_IW_FB_CUR] = 0;
         }
 
-        template<bool COUNT, bool FB = false>
+        template<bool COUNT>
         __global__ void __launch_bounds__(256, CRB_TRACE2_OCC) k_shadow2(DScene sc, PathState ps)
         {
-            const uint32_t n = ps.counters[FB ? CTR_IW_FB : CTR_SHADOW];
+            const uint32_t n = ps.counters[CTR_SHADOW];
             TravCounters   tc;
             auto source = [&](uint32_t idx, uint32_t &item, V3 &o, V3 &d, float &tmin, float &tmax) {
-                if (FB) idx = ps.iw_fb[idx];
                 item            = idx;
                 const float4 so = ld_stream(&ps.shadow[idx].o), sd = ld_stream(&ps.shadow[idx].d);
                 o = v3(so.x, so.y, so.z), d = v3(sd.x, sd.y, sd.z);
@@ -1255,7 +1198,7 @@ namespace crb
                     ps.rad[slot]        = make_float4(r.x, r.y, r.z, 0.f);
                 }
             };
-            trace_persistent_2l<COUNT, CRB_TRACE2_STEPS, true>(sc.bvh2, ps.counters + (FB ? CTR_IW_FB_CUR : CTR_CUR_SHADOW), n, true, source, sink, &tc);
+            trace_persistent_2l<COUNT, CRB_TRACE2_STEPS, true>(sc.bvh2, ps.counters + CTR_CUR_SHADOW, n, true, source, sink, &tc);
             if (COUNT)
             {
                 atomicAdd(ps.stats + ST_NODES_SHADOW, tc.nodes);
@@ -1701,25 +1644,24 @@ namespace crb
                     // closest hit as a wavefront over instance visits: candidates, then IW_K rounds of (single-level loop over the
                     // items, merge + next candidate), then the general loop over the rays with more than IW_K candidates
                     if (count)
-                        CRB_LAUNCH((k_iw_candidates<true, false>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_iw_candidates<true>), pgrid, pblock, st, dscene, ps);
                     else
-                        CRB_LAUNCH((k_iw_candidates<false, false>), pgrid, pblock, st, dscene, ps);
+                        CRB_LAUNCH((k_iw_candidates<false>), pgrid, pblock, st, dscene, ps);
                     for (int round = 0; round < IW_K; round++)
                     {
                         const int q = round & 1;
                         if (count)
-                            CRB_LAUNCH((k_iw_trace<true>), tgrid, tblock, st, dscene, ps, q, 0);
+                            CRB_LAUNCH((k_iw_trace<true>), tgrid, tblock, st, dscene, ps, q);
                         else
-                            CRB_LAUNCH((k_iw_trace<false>), tgrid, tblock, st, dscene, ps, q, 0);
+                            CRB_LAUNCH((k_iw_trace<false>), tgrid, tblock, st, dscene, ps, q);
                         CRB_LAUNCH(k_iw_next, pgrid, pblock, st, dscene, ps, q, round);
-                        CRB_LAUNCH(k_iw_roll, 1, 1, st, ps, q, 0);
+                        CRB_LAUNCH(k_iw_roll, 1, 1, st, ps, q);
                     }
                     if (count)
                         CRB_LAUNCH((k_trace2<true, true>), t2grid, pblock, st, dscene, ps);
                     else
                         CRB_LAUNCH((k_trace2<false, true>), t2grid, pblock, st, dscene, ps);
-                    CRB_LAUNCH(k_iw_roll, 1, 1, st, ps, 0, 1);    // the fallback queue is reused by the shadow rays
-                    launches += 2 + 3 * IW_K;
+                    launches += 1 + 3 * IW_K;
                 }
                 else if (dscene.two_level)
                 {
@@ -1756,29 +1698,6 @@ namespace crb
                             CRB_LAUNCH((k_shadow_alpha<true>), pgrid, pblock, st, dscene, ps);
                         else
                             CRB_LAUNCH((k_shadow_alpha<false>), pgrid, pblock, st, dscene, ps);
-                    }
-                    else if (dscene.two_level && iw && !(flags & CRB_RENDER_FLAG_EXTENDED))
-                    {
-                        // the sun's shadow rays (unbounded, the only kind of the ref-exact mode) as any-hit items of the instance wavefront
-                        if (count)
-                            CRB_LAUNCH((k_iw_candidates<true, true>), pgrid, pblock, st, dscene, ps);
-                        else
-                            CRB_LAUNCH((k_iw_candidates<false, true>), pgrid, pblock, st, dscene, ps);
-                        for (int round = 0; round < IW_K; round++)
-                        {
-                            const int q = round & 1;
-                            if (count)
-                                CRB_LAUNCH((k_iw_trace<true>), tgrid, tblock, st, dscene, ps, q, 1);
-                            else
-                                CRB_LAUNCH((k_iw_trace<false>), tgrid, tblock, st, dscene, ps, q, 1);
-                            CRB_LAUNCH(k_iw_next_shadow, pgrid, pblock, st, dscene, ps, q, round);
-                            CRB_LAUNCH(k_iw_roll, 1, 1, st, ps, q, 0);
-                        }
-                        if (count)
-                            CRB_LAUNCH((k_shadow2<true, true>), t2grid, pblock, st, dscene, ps);
-                        else
-                            CRB_LAUNCH((k_shadow2<false, true>), t2grid, pblock, st, dscene, ps);
-                        launches += 1 + 3 * IW_K;
                     }
                     else if (dscene.two_level)
                     {
