@@ -611,7 +611,8 @@ def partitioned_config(a, ctx, api, scenes, D, desc, w, h, bounces, total_spp, n
         # ncu figures: the flattened tree runs k_trace, the two-level default k_trace2 (separate committed captures)
         out["roofline"] = trace_roofline(api, make_r, 16, 2, device_l2_bytes(api), g, ("c4_k_trace" if flatten else "c4tl_k_trace") + "_dram_bytes_per_launch")
         if not flatten and any(m.instances is not None for m in desc.meshes):
-            out["roofline"]["kernel"] = "k_trace2 (closest-hit traversal, two-level)"
+            out["roofline"]["kernel"] = ("closest-hit pass of the two-level scene: instance wavefront k_iw_candidates + 8 x (k_iw_trace, k_iw_next) + fallback k_trace2, "
+                                         "timed as one launch per bounce; the persistent loop it replaces (CRB_INSTANCE_WAVEFRONT=0) is profiled in profiles/r2ad_c4tl_k_trace2.md")
     return out
 
 
