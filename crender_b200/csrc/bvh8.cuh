@@ -4,7 +4,7 @@
 // rtcIntersect1 query (src/objects/model.cpp:27). B200 has no RT cores; this is a software BVH laid
 // out for 16-byte vector loads from L2/HBM:
 //
-//   node  = 80 bytes = five uint4 loads:
+//   node  = 80 bytes in a 32-byte-aligned 96-byte slot = three 256-bit loads (CRB_NODE_U4; five 16-byte words used):
 //     n0: origin.xyz (f32) | ex,ey,ez (biased power-of-two exponents) , imask (bit s: slot s is an inner node)
 //     n1: child_base (index of first inner child, < 2^24) | tri_base (index of first leaf triangle) | meta[8]
 //     n2: qlo.x[8] | qlo.y[8]        8-bit child boxes on the grid origin + q * 2^(e-127)
@@ -51,17 +51,37 @@
 #define CRB_TP_SMEM 1
 #endif
 
+// Node slot in memory, in 16-byte words: 5 = the packed 80-byte record read by five 128-bit loads; 6 = the same record
+// in a 32-byte-aligned 96-byte slot read by THREE 256-bit loads (sm_100's LDG.E.ENL2.256). The secondary-ray launches of
+// the trace loop run the L1's tag stage at 92 % (profiles/r2p_k_trace.md): every load instruction of a divergent warp is
+// one pass per active lane, whatever its width, so fewer, wider loads per node are fewer passes; an aligned 96-byte slot
+// also touches exactly three 32-byte sectors where an 80-byte record at a 16-byte boundary touches 3 or 4. Measured
+// +1.5 % on config 2 (profiles/r2_sweeps.md section 14).
+#ifndef CRB_NODE_U4
+#define CRB_NODE_U4 6
+#endif
+// Triangle slot, in 16-byte words: 3 = the packed 48-byte record (three 128-bit loads); 4 = a 64-byte slot read by two
+// 256-bit loads (same reasoning; +16 bytes per triangle of L2 footprint: measured 0.9 % slower, profiles/r2_sweeps.md
+// section 14).
+#ifndef CRB_TRI_F4
+#define CRB_TRI_F4 3
+#endif
+
 namespace crb
 {
     constexpr int      BVH8_STACK      = 48;     // entries; the builder rejects deeper trees loudly
     constexpr int      BVH8_LEAF_TRIS  = 3;      // max triangles per leaf child
     constexpr uint32_t INVALID_PRIM    = 0xffffffffu;
     constexpr float    BVH8_BOX_SLACK  = 1.000001f;    // relative loosening of the slab exit distance
+    constexpr int      BVH8_NODE_U4    = CRB_NODE_U4;  // uint4 words per node slot (5 packed, 6 = 32-byte aligned)
+    static_assert(BVH8_NODE_U4 == 5 || BVH8_NODE_U4 == 6, "node slot is 80 or 96 bytes");
+    constexpr int      BVH8_TRI_F4     = CRB_TRI_F4;   // float4 words per triangle slot (3 packed, 4 = 64-byte aligned)
+    static_assert(BVH8_TRI_F4 == 3 || BVH8_TRI_F4 == 4, "triangle slot is 48 or 64 bytes");
 
     struct Bvh8
     {
-        const uint4  *nodes;    // 5 per node
-        const float4 *tris;     // 3 per triangle
+        const uint4  *nodes;    // BVH8_NODE_U4 per node (the record is the first five)
+        const float4 *tris;     // BVH8_TRI_F4 per triangle (the record is the first three)
         uint32_t      n_nodes;
         uint32_t      n_tris;
     };
@@ -150,6 +170,43 @@ namespace crb
         float4 v;
         asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
         return v;
+#endif
+    }
+
+    // The three words of triangle `index` (see CRB_TRI_F4); the loads stay together like ldg128_pinned's.
+    __device__ __forceinline__ void load_tri(const float4 *tris, size_t index, float4 &a, float4 &b, float4 &c)
+    {
+        const float4 *tp = tris + index * BVH8_TRI_F4;
+#if CRB_TRI_F4 == 4 && !defined(CRB_EMU)
+        float p0, p1, p2, p3;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                     : "l"(tp));
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w), "=f"(p0), "=f"(p1), "=f"(p2), "=f"(p3)
+                     : "l"(tp + 2));
+#else
+        a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
+#endif
+    }
+
+    // The five words of node `index` (see CRB_NODE_U4).
+    __device__ __forceinline__ void load_node(const uint4 *nodes, size_t index, uint4 &n0, uint4 &n1, uint4 &n2, uint4 &n3, uint4 &n4)
+    {
+        const uint4 *np = nodes + index * BVH8_NODE_U4;
+#if CRB_NODE_U4 == 6 && !defined(CRB_EMU)
+        unsigned pad0, pad1, pad2, pad3;
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(n0.x), "=r"(n0.y), "=r"(n0.z), "=r"(n0.w), "=r"(n1.x), "=r"(n1.y), "=r"(n1.z), "=r"(n1.w)
+            : "l"(np));
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(n2.x), "=r"(n2.y), "=r"(n2.z), "=r"(n2.w), "=r"(n3.x), "=r"(n3.y), "=r"(n3.z), "=r"(n3.w)
+            : "l"(np + 2));
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(n4.x), "=r"(n4.y), "=r"(n4.z), "=r"(n4.w), "=r"(pad0), "=r"(pad1), "=r"(pad2), "=r"(pad3)
+            : "l"(np + 4));
+#else
+        n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 #endif
     }
 
@@ -311,15 +368,15 @@ namespace crb
             const unsigned node_index = pop_inner(group, oct4);
             if (group.y) stack[sp++] = group;
 
-            const uint4 *np = bvh.nodes + size_t(node_index) * 5;
-            const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            uint4 n0, n1, n2, n3, n4;
+            load_node(bvh.nodes, node_index, n0, n1, n2, n3, n4);
             if (COUNT) ctr->nodes++;
             node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, best.t, group, tgroup, occ);
 
             while (tgroup.y)
             {
-                const float4 *tp = bvh.tris + size_t(pop_triangle(tgroup, occ)) * 3;
-                const float4  a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float4 a, b, c;
+                load_tri(bvh.tris, pop_triangle(tgroup, occ), a, b, c);
                 if (COUNT) ctr->tris++;
                 float t, u, v;
                 if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, best.t, t, u, v))
@@ -464,8 +521,8 @@ namespace crb
                     const unsigned node_index = pop_inner(group, oct4);
                     if (group.y) stack[sp++] = group;
 
-                    const uint4 *np = bvh.nodes + (OFFSETS ? size_t(node_off) + node_index : size_t(node_index)) * 5;
-                    const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                    uint4 n0, n1, n2, n3, n4;
+                    load_node(bvh.nodes, OFFSETS ? size_t(node_off) + node_index : size_t(node_index), n0, n1, n2, n3, n4);
                     if (COUNT) ctr->nodes++;
                     node_visit(n0, n1, n2, n3, n4, o, idir, oct4, tmin, best_t, group, tgroup, occ);
                 }
@@ -501,8 +558,8 @@ namespace crb
                     if (pending)
                     {
                         const float4  dq = r_dir;
-                        const float4 *tp = bvh.tris + (OFFSETS ? size_t(__float_as_uint(dq.w)) + pop_triangle(tgroup, occ) : size_t(pop_triangle(tgroup, occ))) * 3;
-                        const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
+                        float4 a, b, c;
+                        load_tri(bvh.tris, OFFSETS ? size_t(__float_as_uint(dq.w)) + pop_triangle(tgroup, occ) : size_t(pop_triangle(tgroup, occ)), a, b, c);
                         if (COUNT) ctr->tris++;
                         float t, u, v;
                         if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, v3(dq.x, dq.y, dq.z), tmin, best_t, t, u, v))
@@ -723,8 +780,8 @@ namespace crb
                 {
                     const unsigned node_index = pop_inner(group, oct4);
                     if (group.y) stack[sp++] = group;
-                    const uint4   *np = (in_blas ? sc.nodes + size_t(node_off) * 5 : sc.tlas.nodes) + size_t(node_index) * 5;
-                    const uint4    n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                    uint4 n0, n1, n2, n3, n4;
+                    load_node(in_blas ? sc.nodes + size_t(node_off) * BVH8_NODE_U4 : sc.tlas.nodes, node_index, n0, n1, n2, n3, n4);
                     if (COUNT) ctr->nodes++;
                     // far limit of the slab test: inside an instance the local best; in the TLAS the best so far (a world
                     // distance when RENORM, the ray parameter otherwise), loosened so that candidates within rounding are kept
@@ -737,8 +794,8 @@ namespace crb
                 {
                     if (pending)
                     {
-                        const float4 *tp = sc.tris + (size_t(tri_off) + pop_triangle(tgroup, occ)) * 3;
-                        const float4  a = ldg128_pinned(tp), b = ldg128_pinned(tp + 1), c = ldg128_pinned(tp + 2);
+                        float4 a, b, c;
+                        load_tri(sc.tris, size_t(tri_off) + pop_triangle(tgroup, occ), a, b, c);
                         if (COUNT) ctr->tris++;
                         float t, u, v;
                         if (tri_test(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), o, d, tmin, loc.t, t, u, v))
@@ -769,7 +826,7 @@ namespace crb
                         if (want)
                         {
                             // the proxy triangle's id is the instance index; the record is nine 16-byte loads
-                            const uint32_t k  = __float_as_uint(__ldg(sc.tlas.tris + size_t(pop_triangle(tgroup, occ)) * 3).w);
+                            const uint32_t k  = __float_as_uint(__ldg(sc.tlas.tris + size_t(pop_triangle(tgroup, occ)) * BVH8_TRI_F4).w);
                             const float4  *ip = reinterpret_cast<const float4 *>(sc.inst + k);
                             const float4   i6 = __ldg(ip + 6), i7 = __ldg(ip + 7);
                             const float    lo[3] = { i6.x, i6.y, i6.z }, hi[3] = { i7.x, i7.y, i7.z };

@@ -476,10 +476,11 @@ namespace crb
                     {
                         const uint32_t prim = c.vals[leaves[q]];
                         const float   *v    = c.wv + size_t(prim) * 9;
-                        float4        *dst  = c.tris + size_t(tri_base + uint32_t(tri_off + q)) * 3;
+                        float4        *dst  = c.tris + size_t(tri_base + uint32_t(tri_off + q)) * BVH8_TRI_F4;
                         dst[0]              = make_float4(v[0], v[1], v[2], __uint_as_float(prim));
                         dst[1]              = make_float4(__fsub_rn(v[3], v[0]), __fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), 0.f);
                         dst[2]              = make_float4(__fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]), __fsub_rn(v[8], v[2]), 0.f);
+                        if (BVH8_TRI_F4 > 3) dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     leaf_area_tris += box_area(clo[j], chi[j]) * float(cnt);
                 }
@@ -493,12 +494,13 @@ namespace crb
             }
 
             auto pack4 = [](const unsigned *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
-            uint4 *np  = c.nodes + size_t(self) * 5;
+            uint4 *np  = c.nodes + size_t(self) * BVH8_NODE_U4;
             np[0]      = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
             np[1]      = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
             np[2]      = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
             np[3]      = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
             np[4]      = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+            if (BVH8_NODE_U4 > 5) np[5] = make_uint4(0u, 0u, 0u, 0u);    // padding of the 32-byte-aligned slot
 
             if (c.root_area > 0.f)
             {
@@ -566,9 +568,10 @@ namespace crb
                 }
                 meta[s]        = 1u;    // a leaf of one triangle
                 const float *v = wv + size_t(j) * 9;
-                tris[j * 3 + 0] = make_float4(v[0], v[1], v[2], __uint_as_float(j));
-                tris[j * 3 + 1] = make_float4(__fsub_rn(v[3], v[0]), __fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), 0.f);
-                tris[j * 3 + 2] = make_float4(__fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]), __fsub_rn(v[8], v[2]), 0.f);
+                tris[j * BVH8_TRI_F4 + 0] = make_float4(v[0], v[1], v[2], __uint_as_float(j));
+                tris[j * BVH8_TRI_F4 + 1] = make_float4(__fsub_rn(v[3], v[0]), __fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), 0.f);
+                tris[j * BVH8_TRI_F4 + 2] = make_float4(__fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]), __fsub_rn(v[8], v[2]), 0.f);
+                if (BVH8_TRI_F4 > 3) tris[j * BVH8_TRI_F4 + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             auto pack4 = [](const unsigned *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
             nodes[0]   = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]), eb[0] | (eb[1] << 8) | (eb[2] << 16));
@@ -576,6 +579,7 @@ namespace crb
             nodes[2]   = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
             nodes[3]   = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
             nodes[4]   = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+            if (BVH8_NODE_U4 > 5) nodes[5] = make_uint4(0u, 0u, 0u, 0u);
         }
 
 #include "bvh_treelet.inl"
@@ -595,8 +599,8 @@ namespace crb
         stats = BuildStats();
         if (n > 0x7ffffff0u) throw Error(ERR_BUILD_INDEX, "too many triangles for 32-bit primitive ids");
         const size_t max_nodes = size_t(n) / 2 + 8;
-        nodes.alloc(max_nodes * 5);
-        tris.alloc(size_t(n ? n : 1) * 3);
+        nodes.alloc(max_nodes * BVH8_NODE_U4);
+        tris.alloc(size_t(n ? n : 1) * BVH8_TRI_F4);
         if (n > 0 && n <= TINY_BVH_MAX && !getenv("CRB_NO_TINY_BVH"))
         {
             // one node, one triangle per slot: a single launch, no host round trip (the stream orders it before any use)
@@ -766,7 +770,7 @@ namespace crb
             if (attempt > 0) throw Error(ERR_GENERIC, "internal: wide node pool overflow");
             // the true bound: every wide inner node consumes at least one binary inner node
             pool_nodes = size_t(n) + 8;
-            nodes.alloc(pool_nodes * 5);
+            nodes.alloc(pool_nodes * BVH8_NODE_U4);
             q_big.alloc(pool_nodes * 2);
             q0 = q_big.p, q1 = q_big.p + pool_nodes;
         }
@@ -785,7 +789,7 @@ namespace crb
             unsigned long long hc[9] = {}, hi_[9] = {}, hl[9] = {}, halves[4] = {};
             for (uint32_t i = 0; i < stats.n_nodes; i++)
             {
-                const uint4 n1 = nodes.p[size_t(i) * 5 + 1];
+                const uint4 n1 = nodes.p[size_t(i) * BVH8_NODE_U4 + 1];
                 int nc = 0, nin = 0, lo4 = 0, hi4 = 0;
                 for (int s = 0; s < 8; s++)
                 {

@@ -213,8 +213,8 @@ int crb_scene_commit(crb_scene *s, crb_build_info *info)
             info->upload_ms   = s->s.upload_ms;
             info->n_triangles = s->s.build.n_tris;
             info->n_nodes     = s->s.build.n_nodes;
-            info->node_bytes  = uint64_t(s->s.build.n_nodes) * 80;
-            info->tri_bytes   = uint64_t(s->s.stored_tris) * 48 + (s->s.two_level ? uint64_t(s->s.n_instances) * (sizeof(crb::Instance) + 48) : 0);
+            info->node_bytes  = uint64_t(s->s.build.n_nodes) * crb::BVH8_NODE_U4 * 16;
+            info->tri_bytes   = uint64_t(s->s.stored_tris) * crb::BVH8_TRI_F4 * 16 + (s->s.two_level ? uint64_t(s->s.n_instances) * (sizeof(crb::Instance) + crb::BVH8_TRI_F4 * 16) : 0);
             info->max_depth   = s->s.build.max_depth;
             info->sah_cost    = s->s.build.sah_cost;
         }

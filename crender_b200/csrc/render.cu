@@ -865,7 +865,7 @@ namespace crb
                 const Instance &I  = sc.bvh2.inst[k];
                 const V3        oo = xf34(I.inv, o, 1.0f), dd = normalize(xf34(I.inv, d, 0.0f));
                 const Blas      bl = sc.bvh2.blas[I.blas];
-                const Bvh8      view { sc.bvh2.nodes + size_t(bl.node_base) * 5, sc.bvh2.tris + size_t(bl.tri_base) * 3, bl.n_nodes, bl.n_tris };
+                const Bvh8      view { sc.bvh2.nodes + size_t(bl.node_base) * BVH8_NODE_U4, sc.bvh2.tris + size_t(bl.tri_base) * BVH8_TRI_F4, bl.n_nodes, bl.n_tris };
                 const Hit       h = traverse<false, COUNT>(view, oo, dd, 0.00001f, inf_f(), tc);
                 if (h.prim == INVALID_PRIM) continue;
                 const float dist = length(xf34(I.fwd, oo + dd * h.t, 1.0f) - o);
@@ -1033,13 +1033,13 @@ namespace crb
                         {
                             const unsigned node_index = pop_inner(group, oct4);
                             if (group.y) stack[sp++] = group;
-                            const uint4 *np = sc.bvh2.tlas.nodes + size_t(node_index) * 5;
-                            const uint4  n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                            uint4 n0, n1, n2, n3, n4;
+                            load_node(sc.bvh2.tlas.nodes, node_index, n0, n1, n2, n3, n4);
                             if (COUNT) nodes++;
                             node_visit(n0, n1, n2, n3, n4, wo, tidir, oct4, 0.0f, inf_f(), group, tgroup, occ);
                             while (tgroup.y)
                             {
-                                const uint32_t k = __float_as_uint(__ldg(sc.bvh2.tlas.tris + size_t(pop_triangle(tgroup, occ)) * 3).w);
+                                const uint32_t k = __float_as_uint(__ldg(sc.bvh2.tlas.tris + size_t(pop_triangle(tgroup, occ)) * BVH8_TRI_F4).w);
                                 if (!iw_consider(sc, k, wo, tidir, ct, ci, nc)) fallback = true;
                             }
                             if (group.y == 0u)

@@ -347,12 +347,12 @@ namespace crb
                 blas_build_ms += st.build_ms, blas_depth = std::max(blas_depth, st.max_depth), sah += st.sah_cost;
                 src_off += models[mi].ntris;
             }
-            d_blas_nodes.alloc(node_total * 5 + 5);
-            d_blas_tris.alloc(tri_total * 3 + 3);
+            d_blas_nodes.alloc(node_total * BVH8_NODE_U4 + BVH8_NODE_U4);
+            d_blas_tris.alloc(tri_total * BVH8_TRI_F4 + BVH8_TRI_F4);
             for (size_t mi = 0; mi < models.size(); mi++)
             {
-                dev_copy(d_blas_nodes.p + size_t(blas_table[mi].node_base) * 5, bn[mi].p, size_t(blas_table[mi].n_nodes) * 80, stream);
-                dev_copy(d_blas_tris.p + size_t(blas_table[mi].tri_base) * 3, bt[mi].p, size_t(blas_table[mi].n_tris) * 48, stream);
+                dev_copy(d_blas_nodes.p + size_t(blas_table[mi].node_base) * BVH8_NODE_U4, bn[mi].p, size_t(blas_table[mi].n_nodes) * BVH8_NODE_U4 * 16, stream);
+                dev_copy(d_blas_tris.p + size_t(blas_table[mi].tri_base) * BVH8_TRI_F4, bt[mi].p, size_t(blas_table[mi].n_tris) * BVH8_TRI_F4 * 16, stream);
             }
             d_blas.alloc(models.size() ? models.size() : 1);
             dev_upload(d_blas.p, blas_table.data(), blas_table.size() * sizeof(Blas), stream);
