@@ -266,9 +266,9 @@ namespace crb
             const float    *wv;
             uint4          *nodes;
             float4         *tris;
-            uint32_t       *counters;    // [0] nodes allocated, [1] tris allocated, [2] out-queue size
+            uint32_t       *counters;    // [0] nodes allocated, [1] tris allocated, [8 + L] queue size of level L (zeroed per build)
             float          *sah;         // accumulated wide-tree SAH cost (area-weighted), informational
-            float           root_area;
+            const float4   *root_hi;     // hi[0] of the binary tree: .w = the root's surface area (null: a single leaf)
             int             use_dp;
             uint32_t        max_nodes;   // capacity of the node pool and of both collapse queues; overflow sets counters[7]
         };
@@ -290,10 +290,17 @@ namespace crb
             return n;
         }
 
-        __global__ void k_collapse(CollapseCtx c, const uint2 *__restrict__ in, uint32_t n_in, uint2 *__restrict__ out)
+        // One level of the wide tree per launch. The level's queue size is read from the device (counters[8 + level]) and the
+        // launch covers the level's upper bound (min(8^level, pool)), so the host can queue a whole group of levels without
+        // reading anything back (round 1 and most of round 2: one blocking 32-byte read per level, ~0.3 ms of a 5 ms build).
+        constexpr uint32_t COLLAPSE_MAX_LEVELS = 72, COLLAPSE_GROUP = 12;
+        __global__ void k_collapse(CollapseCtx c, const uint2 *__restrict__ in, uint32_t level, uint2 *__restrict__ out)
         {
             const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-            if (w >= n_in) return;
+            uint32_t       n_in = c.counters[8 + level];
+            n_in                = n_in < c.max_nodes ? n_in : c.max_nodes;
+            // an overflow flagged by an earlier level: the host re-runs the stage, nothing below is worth writing
+            if (w >= n_in || *(volatile uint32_t *) (c.counters + 7)) return;
             const int      root = int(in[w].x);
             const uint32_t self = in[w].y;
 
@@ -399,7 +406,7 @@ namespace crb
             }
             const uint32_t child_base = n_inner ? atomicAdd(c.counters + 0, uint32_t(n_inner)) : 0u;
             const uint32_t tri_base   = n_ltris ? atomicAdd(c.counters + 1, uint32_t(n_ltris)) : 0u;
-            const uint32_t out_base   = n_inner ? atomicAdd(c.counters + 2, uint32_t(n_inner)) : 0u;
+            const uint32_t out_base   = n_inner ? atomicAdd(c.counters + 9 + level, uint32_t(n_inner)) : 0u;
             // n/2+8 nodes hold for the greedy collapse (a non-full node has only leaf children); the DP collapse can
             // plateau (C(m,j) == C(m,j-1)) and emit thinner nodes. Never write past the pool / queues: flag, and the
             // host rebuilds this stage with the true bound (every wide inner node consumes a binary inner node: <= n)
@@ -502,10 +509,11 @@ namespace crb
             np[4]      = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
             if (BVH8_NODE_U4 > 5) np[5] = make_uint4(0u, 0u, 0u, 0u);    // padding of the 32-byte-aligned slot
 
-            if (c.root_area > 0.f)
+            const float root_area = c.root_hi ? c.root_hi->w : 0.f;
+            if (root_area > 0.f)
             {
                 const float na = 2.0f * ((nhi[0] - nlo[0]) * (nhi[1] - nlo[1]) + (nhi[1] - nlo[1]) * (nhi[2] - nlo[2]) + (nhi[2] - nlo[2]) * (nhi[0] - nlo[0]));
-                atomicAdd(c.sah, (SAH_CI * na + SAH_CT * leaf_area_tris) / c.root_area);
+                atomicAdd(c.sah, (SAH_CI * na + SAH_CT * leaf_area_tris) / root_area);
             }
         }
 
@@ -629,7 +637,7 @@ namespace crb
         sz(n, 8), sz(n, 8), sz(n, 4), sz(n, 4);    // keys x2, vals x2
         sz(ni, 4), sz(ni, 4), sz(ni, 4), sz(n, 4), sz(ni, 4), sz(ni, 16), sz(ni, 16), sz(ni, 4), sz(ni, 28), sz(ni, 8);    // tree + collapse DP tables
         sz(max_nodes, 8), sz(max_nodes, 8);   // collapse queues
-        sz(8, 4);                             // counters + sah
+        sz(8 + COLLAPSE_MAX_LEVELS + 8, 4);   // counters + sah + per-level queue sizes of the collapse + treelet counter
 #ifndef CRB_EMU
         sz(radix_sort_hist_entries(n), 4);    // radix sort histograms
 #endif
@@ -659,7 +667,7 @@ namespace crb
         t.dpc        = carve<float>(p, ni * 7);
         t.dpk        = carve<unsigned char>(p, ni * 8);
         uint2    *q0_small = carve<uint2>(p, max_nodes), *q1_small = carve<uint2>(p, max_nodes);
-        uint32_t *counters = carve<uint32_t>(p, 8);
+        uint32_t *counters = carve<uint32_t>(p, 8 + COLLAPSE_MAX_LEVELS + 8);
 #ifndef CRB_EMU
         uint32_t *rs_hist = carve<uint32_t>(p, radix_sort_hist_entries(n));
 #endif
@@ -703,8 +711,8 @@ namespace crb
 #endif
 
         // ---- K2
-        float root_area = 0.f;
         int   root_ref  = ~0;    // single triangle: the root reference is leaf 0
+        bool  treelets_ran = false;
         if (n > 1)
         {
             dev_zero(t.flags, ni * sizeof(int), stream);
@@ -713,14 +721,12 @@ namespace crb
             // ---- K3
             if (opt.treelet_passes > 0 && n >= 16)
             {
-                dev_zero(counters + 5, 4, stream);
-                treelet_optimize(t, int(n), plo, phi, vals, stream, opt.treelet_passes, counters + 5);
-                dev_download(&stats.treelets_changed, counters + 5, 4, stream);
+                // the count of changed treelets is read back with the collapse's counters (no round trip of its own)
+                dev_zero(counters + 8 + COLLAPSE_MAX_LEVELS, 4, stream);
+                treelet_optimize(t, int(n), plo, phi, vals, stream, opt.treelet_passes, counters + 8 + COLLAPSE_MAX_LEVELS);
+                treelets_ran = true;
             }
-            float4 hi0;
-            dev_download(&hi0, t.hi, sizeof(float4), stream);
-            root_area = hi0.w;
-            root_ref  = 0;
+            root_ref = 0;
         }
 
         // ---- K4
@@ -728,17 +734,18 @@ namespace crb
         uint2   *q0 = q0_small, *q1 = q1_small;
         DBuf<uint2> q_big;
         uint32_t depth = 0;
+        uint32_t cnt[8 + COLLAPSE_MAX_LEVELS + 8] = {};    // the collapse's counters as of its last group of levels (+ the treelet counter)
         for (int attempt = 0;; attempt++)
         {
             {
-                uint32_t init[8] = { 1, 0, 0, 0, 0, 0, 0, 0 };    // node 0 = root is pre-allocated
+                uint32_t init[8 + COLLAPSE_MAX_LEVELS] = { 1, 0, 0, 0, 0, 0, 0, 0, 1 };    // node 0 = root is pre-allocated; level 0 = the root
                 dev_upload(counters, init, sizeof(init), stream);
                 uint2 first = make_uint2(unsigned(root_ref), 0u);
                 dev_upload(q0, &first, sizeof(first), stream);
             }
             CollapseCtx c;
             c.t = t, c.plo = plo, c.phi = phi, c.vals = vals, c.wv = d_wverts, c.nodes = nodes.p, c.tris = tris.p;
-            c.counters = counters, c.sah = reinterpret_cast<float *>(counters + 4), c.root_area = root_area;
+            c.counters = counters, c.sah = reinterpret_cast<float *>(counters + 4), c.root_hi = n > 1 ? t.hi : nullptr;
             c.use_dp    = (opt.optimal_collapse && n > 1) ? 1 : 0;
             c.max_nodes = uint32_t(pool_nodes);
             if (c.use_dp && attempt == 0)
@@ -746,25 +753,29 @@ namespace crb
                 dev_zero(t.flags, ni * sizeof(int), stream);
                 CRB_LAUNCH(k_collapse_dp, gn, B, stream, int(n), t, plo, phi, vals, opt.cost_prim);
             }
-            uint32_t n_in = 1;
             bool     overflow = false;
             uint2   *qin = q0, *qout = q1;
-            depth = 0;
-            while (n_in)
+            uint32_t level = 0;
+            depth          = 0;
+            for (bool done = false; !done;)
             {
-                depth++;
-                CRB_LAUNCH(k_collapse, (n_in + 127) / 128, 128, stream, c, qin, n_in, qout);
-                uint32_t cnt[8];
+                // a group of levels without a host round trip: level L has at most min(8^L, pool) entries
+                for (uint32_t g = 0; g < COLLAPSE_GROUP && level + 1 < COLLAPSE_MAX_LEVELS; g++, level++)
+                {
+                    const size_t bound = level < 8 ? std::min<size_t>(size_t(1) << (3 * level), pool_nodes) : pool_nodes;
+                    CRB_LAUNCH(k_collapse, unsigned((bound + 127) / 128), 128, stream, c, qin, level, qout);
+                    std::swap(qin, qout);
+                }
                 dev_download(cnt, counters, sizeof(cnt), stream);
                 if (cnt[7] || cnt[0] > pool_nodes)
                 {
                     overflow = true;
                     break;
                 }
-                n_in = cnt[2];
-                const uint32_t zero = 0;
-                dev_upload(counters + 2, &zero, 4, stream);
-                std::swap(qin, qout);
+                depth = 0;
+                while (depth < level && cnt[8 + depth]) depth++;
+                done = cnt[8 + level] == 0;    // the next level's queue is empty
+                if (!done && level + 1 >= COLLAPSE_MAX_LEVELS) throw Error(ERR_BVH_DEPTH, "BVH deeper than " + std::to_string(COLLAPSE_MAX_LEVELS) + " levels");
             }
             if (!overflow) break;
             if (attempt > 0) throw Error(ERR_GENERIC, "internal: wide node pool overflow");
@@ -774,10 +785,9 @@ namespace crb
             q_big.alloc(pool_nodes * 2);
             q0 = q_big.p, q1 = q_big.p + pool_nodes;
         }
-        uint32_t fin[5];
-        dev_download(fin, counters, sizeof(fin), stream);
-        stats.n_nodes = fin[0], stats.n_tris = fin[1], stats.max_depth = depth;
-        memcpy(&stats.sah_cost, &fin[4], 4);
+        stats.n_nodes = cnt[0], stats.n_tris = cnt[1], stats.max_depth = depth;
+        if (treelets_ran) stats.treelets_changed = cnt[8 + COLLAPSE_MAX_LEVELS];
+        memcpy(&stats.sah_cost, &cnt[4], 4);
         if (stats.n_tris != n) throw Error(ERR_GENERIC, "internal: triangle count mismatch after collapse");
         if (stats.n_nodes > 0x00ffffffu) throw Error(ERR_BUILD_INDEX, "too many BVH nodes for the 24-bit child index of the traversal's stack entry");
         if (depth > uint32_t(BVH8_STACK)) throw Error(ERR_BVH_DEPTH, "BVH depth " + std::to_string(depth) + " exceeds the traversal stack");
