@@ -757,10 +757,12 @@ namespace crb
             uint2   *qin = q0, *qout = q1;
             uint32_t level = 0;
             depth          = 0;
+            uint32_t group = COLLAPSE_GROUP;
+            if (const char *e = getenv("CRB_COLLAPSE_GROUP")) group = uint32_t(std::max(1, atoi(e)));    // tests: trees deeper than one group
             for (bool done = false; !done;)
             {
                 // a group of levels without a host round trip: level L has at most min(8^L, pool) entries
-                for (uint32_t g = 0; g < COLLAPSE_GROUP && level + 1 < COLLAPSE_MAX_LEVELS; g++, level++)
+                for (uint32_t g = 0; g < group && level + 1 < COLLAPSE_MAX_LEVELS; g++, level++)
                 {
                     const size_t bound = level < 8 ? std::min<size_t>(size_t(1) << (3 * level), pool_nodes) : pool_nodes;
                     CRB_LAUNCH(k_collapse, unsigned((bound + 127) / 128), 128, stream, c, qin, level, qout);

@@ -808,6 +808,39 @@ def check_tiny_models(oracle, lib_path):
             np.testing.assert_array_equal(g.occluded(rays).astype(bool), hg["prim"] != common.MISS)
 
 
+def check_collapse_groups(oracle, lib_path):
+    """The wide-tree collapse queues its levels in groups without reading anything back (bvh_build.cu, COLLAPSE_GROUP = 12 levels;
+    no tree of the test scenes is deeper than one group): with groups of 1 and 3 levels the continuation after a group's
+    read-back runs too. Same tree statistics, same hits as the default and as the oracle."""
+    desc = scenes.mesh_scene(60, 40, seed=3)
+    rays = common.mixed_rays(desc, 6000, seed=17)
+    ref, infos = None, []
+    old = os.environ.get("CRB_COLLAPSE_GROUP")
+    try:
+        for grp in (None, "1", "3"):
+            if grp is None:
+                os.environ.pop("CRB_COLLAPSE_GROUP", None)
+            else:
+                os.environ["CRB_COLLAPSE_GROUP"] = grp
+            o, g = build_pair(oracle, lib_path, desc)
+            info = g.build_info
+            infos.append((int(info.n_nodes), int(info.max_depth), int(info.n_triangles)))
+            hg = g.cast_rays(rays)
+            if ref is None:
+                ref = hg
+                ho = o.cast_rays(rays)
+                for f in ("prim", "t", "u", "v"):
+                    np.testing.assert_array_equal(hg[f], ho[f], err_msg=f)
+            for f in ("prim", "t", "u", "v"):
+                np.testing.assert_array_equal(hg[f], ref[f], err_msg=f"group {grp} {f}")
+    finally:
+        if old is None:
+            os.environ.pop("CRB_COLLAPSE_GROUP", None)
+        else:
+            os.environ["CRB_COLLAPSE_GROUP"] = old
+    assert infos[0][1] >= 4 and infos[0] == infos[1] == infos[2], infos
+
+
 IW_HASH_SNIPPET = r"""
 import sys, hashlib
 import numpy as np

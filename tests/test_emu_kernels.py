@@ -91,3 +91,7 @@ def test_tiny_models(oracle, emu_lib):
 
 def test_instance_wavefront_equals_loop(emu_lib):
     pc.check_instance_wavefront_equals_loop(emu_lib)
+
+
+def test_collapse_groups(oracle, emu_lib):
+    pc.check_collapse_groups(oracle, emu_lib)

@@ -224,6 +224,10 @@ def test_instance_wavefront_equals_loop(product_lib):
     pc.check_instance_wavefront_equals_loop(product_lib)
 
 
+def test_collapse_groups(oracle, product_lib):
+    pc.check_collapse_groups(oracle, product_lib)
+
+
 def test_against_golden_fixtures(product_lib):
     """The CUDA path against the committed fixtures (no oracle at run time for this test)."""
     import os
