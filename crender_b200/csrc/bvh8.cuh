@@ -50,6 +50,15 @@
 #ifndef CRB_TP_SMEM
 #define CRB_TP_SMEM 1
 #endif
+// Any-hit queries visit the hit children of a node BACK to front. A shadow ray starts on a surface and leaves it: the boxes
+// around its origin are the ones least likely to hold an occluder (the ray grazes its own neighbourhood), yet front-to-back
+// order visits them first. On config 2, 71 % of the sun's shadow rays are occluded (NEE at every hit, also inside the glass
+// and on the night side) and needed 18.2 node visits each to find an occluder front to back, 11.7 back to front: 13.9 -> 9.0
+// node visits and 4.3 -> 2.8 triangle tests per shadow query (kernel-logic harness, tools/tree_quality.py). The answer of an
+// any-hit query does not depend on the order.
+#ifndef CRB_ANY_BACK_FIRST
+#define CRB_ANY_BACK_FIRST 1
+#endif
 
 // Node slot in memory, in 16-byte words: 5 = the packed 80-byte record read by five 128-bit loads; 6 = the same record
 // in a 32-byte-aligned 96-byte slot read by THREE 256-bit loads (sm_100's LDG.E.ENL2.256). The secondary-ray launches of
@@ -326,9 +335,10 @@ namespace crb
     }
 
     // the front-most unvisited inner child of a node group: removes it from the group, returns its node index
-    __device__ __forceinline__ unsigned pop_inner(uint2 &group, unsigned oct4)
+    // back = true takes the BACK-most one instead (any-hit queries, CRB_ANY_BACK_FIRST).
+    __device__ __forceinline__ unsigned pop_inner(uint2 &group, unsigned oct4, bool back = false)
     {
-        const int bit = 31 - __clz(int(group.y));
+        const int bit = back ? __ffs(int(group.y)) - 1 : 31 - __clz(int(group.y));
         group.y &= ~(1u << bit);
         const unsigned slot = (unsigned(bit >> 2) ^ oct4) & 7u;
         return (group.x & 0x00ffffffu) + __popc((group.x >> 24) & ((1u << slot) - 1u));
@@ -364,8 +374,8 @@ namespace crb
 
         for (;;)
         {
-            // pop the front-most unvisited inner child of the current group
-            const unsigned node_index = pop_inner(group, oct4);
+            // pop the front-most (any-hit: back-most) unvisited inner child of the current group
+            const unsigned node_index = pop_inner(group, oct4, CRB_ANY_BACK_FIRST && ANY);
             if (group.y) stack[sp++] = group;
 
             uint4 n0, n1, n2, n3, n4;
@@ -518,7 +528,7 @@ namespace crb
                 // ---- node phase: lanes without pending triangles visit one node
                 if (active && tgroup.y == 0u)
                 {
-                    const unsigned node_index = pop_inner(group, oct4);
+                    const unsigned node_index = pop_inner(group, oct4, CRB_ANY_BACK_FIRST && any);
                     if (group.y) stack[sp++] = group;
 
                     uint4 n0, n1, n2, n3, n4;
@@ -778,7 +788,7 @@ namespace crb
                 const bool do_node = active && tgroup.y == 0u && group.y != 0u;
                 if (do_node)
                 {
-                    const unsigned node_index = pop_inner(group, oct4);
+                    const unsigned node_index = pop_inner(group, oct4, CRB_ANY_BACK_FIRST && any);
                     if (group.y) stack[sp++] = group;
                     uint4 n0, n1, n2, n3, n4;
                     load_node(in_blas ? sc.nodes + size_t(node_off) * BVH8_NODE_U4 : sc.tlas.nodes, node_index, n0, n1, n2, n3, n4);
