@@ -1607,6 +1607,7 @@ namespace crb
 
         const bool count = (flags & CRB_RENDER_FLAG_COUNTERS) != 0;
         static const int steps = getenv("CRB_TRACE_STEPS") ? atoi(getenv("CRB_TRACE_STEPS")) : TRACE_STEPS;    // tuning knob
+        static const int ssteps = getenv("CRB_SHADOW_STEPS") ? atoi(getenv("CRB_SHADOW_STEPS")) : steps;    // ... of the shadow-ray loop alone
 #ifdef CRB_EMU
         const unsigned pgrid = 1, pblock = 1, tgrid = 1, tblock = 1, t2grid = 1, sgrid = 1, sblock = 1;
 #else
@@ -1708,11 +1709,11 @@ namespace crb
                     }
                     else if (count)
                         CRB_LAUNCH((k_shadow<true, TRACE_STEPS>), tgrid, tblock, st, dscene, ps);
-                    else if (steps == 1)
+                    else if (ssteps == 1)
                         CRB_LAUNCH((k_shadow<false, 1>), tgrid, tblock, st, dscene, ps);
-                    else if (steps == 2)
+                    else if (ssteps == 2)
                         CRB_LAUNCH((k_shadow<false, 2>), tgrid, tblock, st, dscene, ps);
-                    else if (steps == 8)
+                    else if (ssteps == 8)
                         CRB_LAUNCH((k_shadow<false, 8>), tgrid, tblock, st, dscene, ps);
                     else
                         CRB_LAUNCH((k_shadow<false, 4>), tgrid, tblock, st, dscene, ps);
