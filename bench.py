@@ -569,7 +569,10 @@ def partitioned_config(a, ctx, api, scenes, D, desc, w, h, bounces, total_spp, n
     kw = dict(seed=0, extended=extended)
     r = ctx.renderer(api, D, w, h, bounces, g, partition=partition, **kw)
     per = max(ctx.world, total_spp // n_steps)
-    r.render(max(ctx.world, min(per, 2 * ctx.world)))  # warm: first launches, allocator, the communicator's first collective
+    # warm: one call of the timed size - first launches, the communicator's first collective, and the per-renderer path state,
+    # which is sized by the first batch (a 2-spp warm-up left its allocation, 13-19 GB per GPU, inside the first timed call:
+    # 43 ms of a 517 ms config-4 run on 8 GPUs)
+    r.render(per)
     r.flush()
     r.start()
 
@@ -584,6 +587,7 @@ def partitioned_config(a, ctx, api, scenes, D, desc, w, h, bounces, total_spp, n
         "passes_per_s": per * n_steps / (ms * 1e-3), "triangles": int(info.n_triangles), "bvh_bytes": int(info.node_bytes + info.tri_bytes),
         "bvh_build_ms": info.build_ms, "scene_upload_ms": info.upload_ms, "gpu_launches": int(launches), "merge": r.info()["merge"], "shading": "extended" if extended else "ref-exact",
         "instances": "flattened into one world-space BVH" if flatten else "two-level (one BLAS per model + TLAS, the reference's per-instance arithmetic)",
+        "warmup": "one untimed call of the same size",
     }
     # end to end: the same calls, wall clock, each followed by an asynchronous read of the merged display into pinned host memory
     outs = [ctx.pinned(h, w) for _ in range(2)]
