@@ -18,7 +18,10 @@ namespace crb
 
     struct BuildOptions
     {
-        int  treelet_passes = 1;       // SAH treelet restructuring sweeps (a second sweep buys <0.5 % rays/s for +11 ms at 1M triangles)
+        // SAH treelet restructuring sweeps. Two: the second costs 2.7 ms at 1 M triangles (build 4.8 -> 7.5 ms) and buys 1.9 % of a
+        // config-2 step (30.7 instead of 31.3 ms per 16 spp: 8.99 -> 8.31 node visits per shadow query, 11.83 -> 11.73 per
+        // closest-hit query), i.e. it pays for itself after five steps; a third buys nothing (profiles/r2_sweeps.md section 19)
+        int  treelet_passes = 2;
         bool optimal_collapse = true;  // SAH-optimal (dynamic programming) binary -> 8-wide collapse; false = greedy by area
         float cost_prim = 0.8f;        // collapse DP: cost of a triangle test relative to an 8-wide node test (swept: profiles/r1c_sweeps.md)
     };
