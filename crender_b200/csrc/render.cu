@@ -263,6 +263,26 @@ namespace crb
             }
         }
 
+#ifdef CRB_EMU
+        // Kernel-logic harness only (compiled out of the product): per-RAY node visits and triangle tests of the counting
+        // instantiations, by query kind and outcome - [kind][outcome] = { rays, node visits, triangle tests, rays that needed at
+        // most one node visit }; kind 0 closest hit (k_trace), 1 shadow (k_shadow); outcome 0 nothing hit, 1 hit. The harness
+        // runs one lane, so the counters' growth between two retirements belongs to one ray. Read by tools/tree_quality.py
+        // through crb_emu_ray_classes; this is how the occluded share of the shadow rays and their cost were found
+        // (profiles/r2_sweeps.md section 17).
+        unsigned long long g_ray_classes[2][2][4];
+        struct RayClassProbe
+        {
+            unsigned long long nodes = 0, tris = 0;
+            void retire(int kind, bool hit, const TravCounters &tc)
+            {
+                unsigned long long *c = g_ray_classes[kind][hit ? 1 : 0];
+                c[0]++, c[1] += tc.nodes - nodes, c[2] += tc.tris - tris, c[3] += (tc.nodes - nodes) <= 1 ? 1 : 0;
+                nodes = tc.nodes, tris = tc.tris;
+            }
+        };
+#endif
+
         // ------------------------------------------------------------------ trace + material sort
         constexpr int TRACE_STEPS = 4;    // node iterations between two refill points of the persistent trace loop
 
@@ -292,7 +312,13 @@ namespace crb
             };
             // retiring a ray is one 16-byte store; the material sort is a separate full-width pass
             // (k_classify) because only a few lanes of a warp retire at any refill point
+#ifdef CRB_EMU
+            RayClassProbe probe;
+#endif
             auto sink = [&](bool valid, uint32_t slot, const Hit &h) {
+#ifdef CRB_EMU
+                if (valid && COUNT) probe.retire(0, h.prim != INVALID_PRIM, tc);
+#endif
                 if (valid) st_stream(ps.hit + slot, make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)));
             };
             trace_persistent<COUNT, STEPS>(sc.bvh, ps.counters + CTR_CUR_TRACE, n, ps.trace_chunk, false, source, sink, &tc);
@@ -1220,7 +1246,13 @@ namespace crb
                 d               = normalize(v3(sd.x, sd.y, sd.z));    // model.cpp:110-112
                 tmin = 0.00001f, tmax = sd.w;                         // inf for the sun, 0.999 * distance for an area light
             };
+#ifdef CRB_EMU
+            RayClassProbe probe;
+#endif
             auto sink = [&](bool valid, uint32_t item, const Hit &h) {
+#ifdef CRB_EMU
+                if (valid && COUNT) probe.retire(1, h.prim != INVALID_PRIM, tc);
+#endif
                 if (valid && h.prim == INVALID_PRIM)
                 {
                     // renderer.cpp:348-353: the sun is visible, connect
@@ -1886,3 +1918,13 @@ namespace crb
         for (int i = 0; i < 8; i++) out.kernel_ms[i] = kernel_ms[i], out.kernel_count[i] = kernel_count[i];
     }
 }    // namespace crb
+
+#ifdef CRB_EMU
+// kernel-logic harness only: the per-ray statistics of RayClassProbe (16 counters), and their reset
+extern "C" void crb_emu_ray_classes(unsigned long long *out16, int reset)
+{
+    for (int i = 0; i < 16; i++) out16[i] = (&crb::g_ray_classes[0][0][0])[i];
+    if (reset)
+        for (int i = 0; i < 16; i++) (&crb::g_ray_classes[0][0][0])[i] = 0;
+}
+#endif
