@@ -52,8 +52,8 @@
 #endif
 // Any-hit queries visit the hit children of a node BACK to front. A shadow ray starts on a surface and leaves it: the boxes
 // around its origin are the ones least likely to hold an occluder (the ray grazes its own neighbourhood), yet front-to-back
-// order visits them first. On config 2, 71 % of the sun's shadow rays are occluded (NEE at every hit, also inside the glass
-// and on the night side) and needed 18.2 node visits each to find an occluder front to back, 11.7 back to front: 13.9 -> 9.0
+// order visits them first. On config 2, 71 % of the sun's shadow rays are occluded (NEE at every hit: inside the glass, in
+// the sphere's shadow) and needed 18.2 node visits each to find an occluder front to back, 11.7 back to front: 13.9 -> 9.0
 // node visits and 4.3 -> 2.8 triangle tests per shadow query (kernel-logic harness, tools/tree_quality.py). The answer of an
 // any-hit query does not depend on the order.
 #ifndef CRB_ANY_BACK_FIRST
@@ -62,8 +62,10 @@
 
 // Node slot in memory, in 16-byte words: 5 = the packed 80-byte record read by five 128-bit loads; 6 = the same record
 // in a 32-byte-aligned 96-byte slot read by THREE 256-bit loads (sm_100's LDG.E.ENL2.256). The secondary-ray launches of
-// the trace loop run the L1's tag stage at 92 % (profiles/r2p_k_trace.md): every load instruction of a divergent warp is
-// one pass per active lane, whatever its width, so fewer, wider loads per node are fewer passes; an aligned 96-byte slot
+// the trace loop keep the L1 data pipe busier than the issue slots (l1tex__data_pipe_lsu_wavefronts 92 % against 73 %,
+// profiles/r2p_k_trace.md): its load is one wavefront per distinct line of every load instruction of a divergent warp plus
+// one per sector filled after a miss. Fewer, wider loads per node: 59.6 M -> 45.5 M load requests and 340 M -> 243 M
+// wavefronts per launch (the fills stay: 0.43 G sectors, the algorithmic bytes), the pipe at 87 %; an aligned 96-byte slot
 // also touches exactly three 32-byte sectors where an 80-byte record at a 16-byte boundary touches 3 or 4. Measured
 // +1.5 % on config 2 (profiles/r2_sweeps.md section 14).
 #ifndef CRB_NODE_U4
